@@ -1,0 +1,181 @@
+/*
+ * mi3d.h -- C ABI of the B200-native Make-It-3D SDS-step hot path (libmi3d.so).
+ *
+ * Drop-in boundary: these entry points are what the reference's pybind module `_raymarching`
+ * (raymarching/src/bindings.cpp:5-23, raymarching/src/raymarching.h:7-22), its third-party tiny-cuda-nn
+ * encoder (nerf/network_tcnn.py:54-65,107) and its diffusers U-Net / VAE calls (nerf/sd.py:117-174,212-220)
+ * would bind instead.  Conventions for every function:
+ *   - plain pointers are DEVICE pointers unless named *_host or documented otherwise; sizes are element counts
+ *   - returns 0 on success, a cudaError_t value or MI3D_ERR_ARG (1000001) otherwise; never throws
+ *   - never allocates device memory and never synchronises; work is enqueued on `stream`
+ *     (pass torch.cuda.current_stream().cuda_stream); scratch comes from the caller, sized by *_workspace_bytes()
+ *   - re-entrant; no global mutable state besides one-time kernel attribute setup
+ *   - all floating-point tensors are fp32 contiguous, exactly as the reference wrappers pass them
+ *     (custom_fwd(cast_inputs=torch.float32), raymarching/raymarching.py:33,175,252)
+ */
+#ifndef MI3D_H
+#define MI3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mi3d_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------------------------------------------
+ * B1: ray-march operators  (replace raymarching/src/raymarching.cu, called from raymarching/raymarching.py)
+ * ------------------------------------------------------------------------------------------------------ */
+
+/* replaces near_far_from_aabb, raymarching.cu:92-160 (wrapper raymarching.py:31-61) */
+int mi3d_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                            float* nears, float* fars, mi3d_stream_t stream);
+
+/* replaces morton3D / morton3D_invert, raymarching.cu:214-258 (raymarching.py:95-142) */
+int mi3d_morton3D(const int* coords, uint32_t N, int* indices, mi3d_stream_t stream);
+int mi3d_morton3D_invert(const int* indices, uint32_t N, int* coords, mi3d_stream_t stream);
+
+/* replaces packbits, raymarching.cu:268-300 (raymarching.py:144-170).  n_bytes = C*H^3/8.
+ * thresh_dev (nullable) is a device scalar: effective threshold = min(thresh, *thresh_dev) -- this is
+ * renderer.py:630 `min(self.mean_density, self.density_thresh)` without the .item() host sync. */
+int mi3d_packbits(const float* grid, uint32_t n_bytes, float thresh, const float* thresh_dev, uint8_t* bitfield,
+                  mi3d_stream_t stream);
+
+/* replaces march_rays_train, raymarching.cu:312-493 (raymarching.py:173-247).
+ *  - nears/fars: precomputed [N] (B1 behaviour) or NULL, in which case the slab test against aabb[6] with
+ *    min_near is fused into the kernel (optionally written to nears_out/fars_out, nullable).
+ *  - noises: [N] U[0,1) (raymarching.py:226) or NULL -> in-kernel Philox keyed by (seed, ray id).
+ *  - rays[n] = (n, offset, count): compaction is ordered by ray id (deterministic), not by atomic arrival.
+ *  - counter[0] += total samples, counter[1] += N (caller zeroes it like renderer.py:504).
+ *  - M = capacity of xyzs/dirs/deltas in rows; rays that do not fit write nothing (raymarching.cu:416).
+ *  - workspace: mi3d_march_rays_train_workspace_bytes(N) bytes (zero-filled internally). */
+size_t mi3d_march_rays_train_workspace_bytes(uint32_t N);
+int mi3d_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield, float bound,
+                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                          const float* nears, const float* fars, const float* aabb, float min_near,
+                          float* nears_out, float* fars_out, const float* noises, uint64_t seed,
+                          float* xyzs, float* dirs, float* deltas, int* rays, int* counter,
+                          void* workspace, mi3d_stream_t stream);
+
+/* Optional fused epilogue of NeRFRenderer.run_cuda (nerf/renderer.py:553-570):
+ *   image_out = image + (1 - ws) * bg ;  depth_out = (depth + (1 - ws) * max_depth) * depth_scale */
+typedef struct {
+    const float* bg_color;    /* device [3] or NULL -> bg_scalar (renderer.py:554-555 default 1) */
+    float bg_scalar;
+    float max_depth;          /* opt.max_depth, main.py:91 */
+    const float* depth_scale; /* device [N] or NULL */
+} mi3d_epilogue;
+
+/* replaces composite_rays_train_forward, raymarching.cu:501-590 (raymarching.py:250-281).
+ * ep == NULL -> plain B1 behaviour (image_out/depth_out ignored). */
+int mi3d_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int* rays,
+                                      uint32_t M, uint32_t N, float T_thresh, float* weights_sum, float* depth,
+                                      float* image, const mi3d_epilogue* ep, float* image_out, float* depth_out,
+                                      mi3d_stream_t stream);
+
+/* replaces composite_rays_train_backward, raymarching.cu:602-696 (raymarching.py:283-300).
+ * grad_image is w.r.t. image (ep == NULL) or image_out (ep != NULL); grad_depth (nullable) is w.r.t. depth_out and
+ * only reaches sigmas through (1 - ws) * max_depth, like autograd does in the reference (raymarching.py:287).
+ * zero_tail != 0 writes zeros to samples after the early-out so the outputs need no pre-zeroing. */
+int mi3d_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* grad_depth,
+                                       const float* sigmas, const float* rgbs, const float* deltas, const int* rays,
+                                       const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                       float T_thresh, const mi3d_epilogue* ep, float* grad_sigmas, float* grad_rgbs,
+                                       int zero_tail, mi3d_stream_t stream);
+
+/* replaces march_rays / composite_rays (inference), raymarching.cu:907-1022, :1024-1125 (raymarching.py:368-470) */
+int mi3d_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o,
+                    const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                    const uint8_t* density_bitfield, const float* nears, const float* fars, float* xyzs, float* dirs,
+                    float* deltas, const float* noises, mi3d_stream_t stream);
+int mi3d_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* rays_alive, float* rays_t,
+                        const float* sigmas, const float* rgbs, const float* normals, const float* deltas,
+                        float* weights_sum, float* depth, float* image, float* normal, mi3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * B2: field  (replaces tinycudann.Encoding + nerf/network_tcnn.py MLP / common_forward / normal / forward)
+ * ------------------------------------------------------------------------------------------------------ */
+
+/* Multiresolution hash grid geometry (tiny-cuda-nn HashGrid as configured at nerf/network_tcnn.py:54-65):
+ * level l owns entries [offsets[l], offsets[l]+sizes[l]) of the flat fp32 table `encoder.params`
+ * (2 features per entry, entry-major). */
+typedef struct {
+    uint32_t n_levels;
+    uint32_t n_entries;
+    uint32_t offsets[16];
+    uint32_t sizes[16];
+    uint32_t ress[16];
+    float scales[16];
+} mi3d_hashgrid;
+
+/* HOST helper: fills *out (host struct, passed by pointer to the calls below). */
+int mi3d_hashgrid_make(uint32_t n_levels, uint32_t base_resolution, double per_level_scale, uint32_t log2_hashmap_size,
+                       mi3d_hashgrid* out);
+
+/* stand-alone encoder: replaces tcnn.Encoding.forward / backward as called at nerf/network_tcnn.py:107.
+ * x [E,3] in [0,1]; out / grad_out [E, 2*n_levels]; grad_table accumulates (+=). hg is a HOST pointer. */
+int mi3d_hashgrid_forward(const float* x, uint32_t E, const float* table, const mi3d_hashgrid* hg, float* out, mi3d_stream_t stream);
+int mi3d_hashgrid_backward(const float* x, uint32_t E, const float* grad_out, const mi3d_hashgrid* hg, float* grad_table, mi3d_stream_t stream);
+
+/* sigma_net = MLP(32, 4, 64, 3) (nerf/network_tcnn.py:67, :13-32): PyTorch nn.Linear layout [out][in], biases on */
+typedef struct { const float *w1, *b1, *w2, *b2, *w3, *b3; } mi3d_mlp;
+typedef struct { float *w1, *b1, *w2, *b2, *w3, *b3; } mi3d_mlp_grad;
+
+enum { MI3D_SHADING_ALBEDO = 0, MI3D_SHADING_LAMBERTIAN = 1, MI3D_SHADING_TEXTURELESS = 2, MI3D_SHADING_NORMAL = 3 };
+
+typedef struct {
+    float bound;          /* opt.bound */
+    float blob_density;   /* opt.blob_density (main.py:56) */
+    float blob_radius;    /* opt.blob_radius  (main.py:57) */
+    int n_evals;          /* 1: sigma/albedo only; 7: + 6-tap finite-difference normal (network_tcnn.py:115-138);
+                             13: + the perturbed normal of the smoothness loss (renderer.py:521-524) */
+    int shading;          /* MI3D_SHADING_* (network_tcnn.py:146-170) */
+    float ambient_ratio;
+    const float* light_d; /* device [3], needed unless shading == albedo */
+} mi3d_field_cfg;
+
+typedef struct {
+    const float* xyzs;         /* [cap,3] sample positions (output of mi3d_march_rays_train) */
+    const float* dirs;         /* [cap,3] or NULL */
+    const int* counter;        /* device: counter[0] = number of valid rows M; NULL -> m_fixed */
+    uint32_t m_fixed;
+    uint32_t align;            /* 128 reproduces the zero-row padding of raymarching.py:237-241 in the loss means; 0 = none */
+    uint32_t cap;              /* rows allocated in every per-sample buffer */
+    const float* smooth_noise; /* [cap,3] N(0,1) (renderer.py:522) or NULL -> in-kernel Philox(seed,row) */
+    uint64_t seed;
+} mi3d_field_io;
+
+/* number of CTAs the persistent field kernels launch; loss_partials must hold 2 * mi3d_field_grid_ctas(0) floats */
+int mi3d_field_grid_ctas(int backward);
+
+/* Fused replacement of NeRFNetwork.forward (+ the regularisers of run_cuda):
+ *   sigmas[row], rgbs[row,3], normals[row,3] (nullable), tape[row,16] (nullable; needed for backward),
+ *   loss_orient / loss_smooth: device scalars (nullable), means over the padded row count like the reference. */
+int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
+                       const mi3d_field_cfg* cfg, float* sigmas, float* rgbs, float* normals, float* tape,
+                       float* loss_partials, float* loss_orient, float* loss_smooth, mi3d_stream_t stream);
+
+/* Backward of the above: accumulates (+=) into grad_table [2*n_entries] and grad_mlp.  grad_* inputs are nullable
+ * (treated as zero); grad_loss_* are device scalars.  No gradient w.r.t. positions (the reference requests none). */
+int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
+                        const mi3d_field_cfg* cfg, const float* tape, const float* grad_sigmas, const float* grad_rgbs,
+                        const float* grad_normals, const float* grad_loss_orient, const float* grad_loss_smooth,
+                        float* grad_table, const mi3d_mlp_grad* grad_mlp, mi3d_stream_t stream);
+
+/* Replaces NeRFRenderer.update_extra_state (nerf/renderer.py:587-637): density_grid [C,H^3] EMA-max update from the
+ * field at jittered cell centres, mean density (device scalar out), bitfield repack.  jitter: [C,H^3,3] U[0,1) or NULL
+ * (Philox).  workspace: mi3d_density_grid_workspace_bytes(C,H). */
+size_t mi3d_density_grid_workspace_bytes(uint32_t C, uint32_t H);
+int mi3d_density_grid_update(float* density_grid, uint8_t* density_bitfield, uint32_t C, uint32_t H, float bound,
+                             float decay, float density_thresh, const float* table, const mi3d_hashgrid* hg,
+                             const mi3d_mlp* mlp, const mi3d_field_cfg* cfg, const float* jitter, uint64_t seed,
+                             float* mean_density_out, void* workspace, mi3d_stream_t stream);
+
+const char* mi3d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MI3D_H */

@@ -1,0 +1,899 @@
+// field.cu -- fused NeRF field evaluation for sm_100a (C ABI: include/mi3d.h)
+//
+// One kernel evaluates, per marched sample, everything nerf/network_tcnn.py:102-170 + nerf/renderer.py:513-524
+// do with 13 separate encoder/MLP passes in the reference:
+//     multires hash-grid gather (tiny-cuda-nn HashGrid, fp32 table)  ->  32-64-64-4 MLP (fp32, bias, ReLU)
+//     -> trunc_exp / sigmoid -> 6-tap finite-difference normal -> shading -> orientation / smoothness terms
+// without ever materialising encodings or activations in HBM.  The backward kernel recomputes the
+// activations tile-by-tile, back-propagates through the MLP, accumulates the weight gradients in registers
+// across the whole persistent CTA, and scatters the table gradient with vector reductions (RED.ADD.v2.f32).
+//
+// Tiling (both kernels): CTA = 256 threads = one tile of T=128 samples.  Activations live in shared memory
+// k-major ([feature][row], row stride TP=132 floats) so that (a) the 32 lanes of a warp read/write 128
+// consecutive rows -> conflict-free LDS.128/STS.128, (b) weights are warp-broadcast LDS.128, (c) the
+// weight-gradient reduction over rows also vectorises along rows without bank conflicts (TP = 4 mod 32).
+// Each thread owns a 4-row x (N/8)-column register tile of every layer GEMM; this is plain fp32 FFMA on
+// purpose: the finite-difference normals difference two densities 0.02 apart, so the MLP needs full fp32
+// (fp16/bf16/tf32 tensor-core inputs would put ~1e-2 relative error on the normals).
+//
+// Grid: persistent, gridDim = 148 SMs x resident CTAs; the number of valid rows is read from device memory
+// (counter[0] written by mi3d_march_rays_train), so there is no host synchronisation between march and field.
+#include "mi3d_common.cuh"
+#include "../../include/mi3d.h"
+
+namespace {
+
+constexpr int T = 128;        // rows (samples) per tile
+constexpr int TP = 132;       // padded row stride of the k-major activation tiles (floats)
+constexpr int NT = 256;       // threads per CTA
+constexpr int D_IN = 32, D_H = 64, D_OUT = 4;
+constexpr float kFdEps = 1e-2f;      // network_tcnn.py:115
+constexpr float kSmoothStd = 1e-2f;  // renderer.py:522
+
+struct LevelSm { uint32_t offset, size, res, hashed; float scale; };
+
+// ---------------------------------------------------------------------------------------------------------
+// hash-grid helpers (tiny-cuda-nn grid.h semantics, see oracle/field_ref.py for the restatement + citations)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hg_index(uint32_t cx, uint32_t cy, uint32_t cz, const LevelSm& L) {
+    uint32_t idx;
+    if (L.hashed) {
+        idx = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+        idx = (L.size & (L.size - 1)) == 0 ? (idx & (L.size - 1)) : (idx % L.size);
+    } else {
+        idx = cx + cy * L.res + cz * L.res * L.res;
+        if (idx >= L.size) idx %= L.size;      // only when a coordinate sits exactly on the upper face
+    }
+    return idx;
+}
+
+struct CellW { uint32_t c[3]; float w[3]; };
+
+__device__ __forceinline__ CellW hg_cell(float u0, float u1, float u2, float scale) {
+    CellW r;
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float p = fmaf(scale, d == 0 ? u0 : (d == 1 ? u1 : u2), 0.5f);
+        const float f = floorf(p);
+        r.c[d] = (uint32_t)(int32_t)f;
+        r.w[d] = p - f;
+    }
+    return r;
+}
+
+// Encode levels [l0, l0+nl) of point u (in [0,1]^3) into enc[(2l+f) * stride + row].
+__device__ __forceinline__ void encode_levels(const float* __restrict__ table, const LevelSm* __restrict__ lv, int l0, int nl,
+                                              float u0, float u1, float u2, float* __restrict__ enc, int stride, int row) {
+    #pragma unroll 2
+    for (int i = 0; i < nl; i++) {
+        const int l = l0 + i;
+        const LevelSm L = lv[l];
+        const CellW cw = hg_cell(u0, u1, u2, L.scale);
+        const float2* __restrict__ base = reinterpret_cast<const float2*>(table) + L.offset;
+        float2 v[8];
+        #pragma unroll
+        for (int corner = 0; corner < 8; corner++) {
+            const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
+            v[corner] = __ldg(base + hg_index(cx, cy, cz, L));
+        }
+        float f0 = 0.f, f1 = 0.f;
+        #pragma unroll
+        for (int corner = 0; corner < 8; corner++) {
+            const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
+            const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
+            const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
+            const float wt = wx * wy * wz;
+            f0 = fmaf(wt, v[corner].x, f0); f1 = fmaf(wt, v[corner].y, f1);
+        }
+        enc[(2 * l) * stride + row] = f0;
+        enc[(2 * l + 1) * stride + row] = f1;
+    }
+}
+
+// Scatter d(enc) of levels [l0,l0+nl) into the table gradient (one RED.v2.f32 per corner).
+__device__ __forceinline__ void scatter_levels(float* __restrict__ gtable, const LevelSm* __restrict__ lv, int l0, int nl,
+                                               float u0, float u1, float u2, const float* __restrict__ genc, int stride, int row) {
+    #pragma unroll 1
+    for (int i = 0; i < nl; i++) {
+        const int l = l0 + i;
+        const LevelSm L = lv[l];
+        const float g0 = genc[(2 * l) * stride + row], g1 = genc[(2 * l + 1) * stride + row];
+        if (g0 == 0.f && g1 == 0.f) continue;
+        const CellW cw = hg_cell(u0, u1, u2, L.scale);
+        float2* __restrict__ base = reinterpret_cast<float2*>(gtable) + L.offset;
+        #pragma unroll
+        for (int corner = 0; corner < 8; corner++) {
+            const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
+            const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
+            const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
+            const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
+            const float wt = wx * wy * wz;
+            atomicAdd(base + hg_index(cx, cy, cz, L), make_float2(wt * g0, wt * g1));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tile GEMMs over shared memory.  A: [K][TP] (k-major), W: [K][N] row-major, Out: [N][TP].
+// thread -> rows lane*4..+3, columns warp*NC..+NC-1 with NC = N/8.
+// MASK: multiply by (mask[n][row] > 0) (ReLU backward; mask may alias Out).
+// ---------------------------------------------------------------------------------------------------------
+template <int K, int N, bool RELU, bool MASK>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                                          float* Out, const float* mask) {
+    constexpr int NC = N / 8;
+    static_assert(NC == 4 || NC == 8, "column tile");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = lane * 4, c0 = warp * NC;
+    float acc[NC][4];
+    #pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const float b = bias ? bias[c0 + c] : 0.f;
+        acc[c][0] = b; acc[c][1] = b; acc[c][2] = b; acc[c][3] = b;
+    }
+    #pragma unroll 8
+    for (int k = 0; k < K; k++) {
+        const float4 a = *reinterpret_cast<const float4*>(A + k * TP + r0);
+        float w[NC];
+        #pragma unroll
+        for (int c4 = 0; c4 < NC / 4; c4++) {
+            const float4 wv = *reinterpret_cast<const float4*>(W + k * N + c0 + 4 * c4);
+            w[4 * c4] = wv.x; w[4 * c4 + 1] = wv.y; w[4 * c4 + 2] = wv.z; w[4 * c4 + 3] = wv.w;
+        }
+        #pragma unroll
+        for (int c = 0; c < NC; c++) {
+            acc[c][0] = fmaf(a.x, w[c], acc[c][0]); acc[c][1] = fmaf(a.y, w[c], acc[c][1]);
+            acc[c][2] = fmaf(a.z, w[c], acc[c][2]); acc[c][3] = fmaf(a.w, w[c], acc[c][3]);
+        }
+    }
+    #pragma unroll
+    for (int c = 0; c < NC; c++) {
+        float4 o = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+        if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (MASK) {
+            const float4 m = *reinterpret_cast<const float4*>(mask + (c0 + c) * TP + r0);
+            o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(Out + (c0 + c) * TP + r0) = o;
+    }
+}
+
+// Output layer 64 -> 4: thread (row = tid & 127, pair = tid >> 7) computes outputs 2*pair, 2*pair+1.
+__device__ __forceinline__ void out_layer(const float* __restrict__ H2, const float* __restrict__ W3t /*[64][4]*/, const float* __restrict__ b3,
+                                          float* __restrict__ O) {
+    const int row = threadIdx.x & (T - 1), pair = threadIdx.x >> 7;
+    float o0 = b3[2 * pair], o1 = b3[2 * pair + 1];
+    #pragma unroll 16
+    for (int k = 0; k < D_H; k++) {
+        const float h = H2[k * TP + row];
+        const float2 w = *reinterpret_cast<const float2*>(W3t + 4 * k + 2 * pair);
+        o0 = fmaf(h, w.x, o0); o1 = fmaf(h, w.y, o1);
+    }
+    O[(2 * pair) * TP + row] = o0; O[(2 * pair + 1) * TP + row] = o1;
+}
+
+// Weight-gradient tile: dW[j][i] += sum_rows P[j][row] * Q[i][row]; thread owns j in {jt + 16a}, i in {it + IT*b}.
+// J = 64 always (16 j-groups x 4); I = 64 (NI=4) or 32 (NI=2).  Also accumulates db[j] on threads with it == 0.
+template <int NI>
+__device__ __forceinline__ void tile_wgrad(const float* __restrict__ P, const float* __restrict__ Q, float (&acc)[4][NI], float (&db)[4]) {
+    const int jt = threadIdx.x >> 4, it = threadIdx.x & 15;
+    #pragma unroll 2
+    for (int s = 0; s < T; s += 4) {
+        float4 p[4], q[NI];
+        #pragma unroll
+        for (int a = 0; a < 4; a++) p[a] = *reinterpret_cast<const float4*>(P + (jt + 16 * a) * TP + s);
+        #pragma unroll
+        for (int b = 0; b < NI; b++) q[b] = *reinterpret_cast<const float4*>(Q + (it + 16 * b) * TP + s);
+        #pragma unroll
+        for (int a = 0; a < 4; a++) {
+            #pragma unroll
+            for (int b = 0; b < NI; b++) {
+                acc[a][b] = fmaf(p[a].x, q[b].x, acc[a][b]); acc[a][b] = fmaf(p[a].y, q[b].y, acc[a][b]);
+                acc[a][b] = fmaf(p[a].z, q[b].z, acc[a][b]); acc[a][b] = fmaf(p[a].w, q[b].w, acc[a][b]);
+            }
+            if (it == 0) db[a] += (p[a].x + p[a].y) + (p[a].z + p[a].w);
+        }
+    }
+}
+
+// dW3[o][i] (4 x 64 = 256 entries, one per thread) and db3 (threads 0..3).
+__device__ __forceinline__ void tile_wgrad3(const float* __restrict__ dO, const float* __restrict__ H2, float& acc, float& db) {
+    const int o = threadIdx.x >> 6, i = threadIdx.x & 63;
+    #pragma unroll 4
+    for (int s = 0; s < T; s += 4) {
+        const float4 p = *reinterpret_cast<const float4*>(dO + o * TP + s);
+        const float4 q = *reinterpret_cast<const float4*>(H2 + i * TP + s);
+        acc = fmaf(p.x, q.x, acc); acc = fmaf(p.y, q.y, acc); acc = fmaf(p.z, q.z, acc); acc = fmaf(p.w, q.w, acc);
+        if (i == 0) db += (p.x + p.y) + (p.z + p.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// shared bookkeeping
+// ---------------------------------------------------------------------------------------------------------
+struct Smem {
+    float* wt1; float* b1; float* wt2; float* b2; float* w3t; float* b3;   // forward layouts [in][out]
+    float* w1; float* w2; float* w3;                                        // backward layouts [out][in] (bwd kernel only)
+    LevelSm* lv;
+    float* enc; float* h1; float* h2; float* o;
+};
+
+__device__ __forceinline__ Smem carve(float* base, bool bwd) {
+    Smem s;
+    float* p = base;
+    s.enc = p; p += D_IN * TP;
+    s.h1 = p; p += D_H * TP;
+    s.h2 = p; p += D_H * TP;
+    s.o = p; p += D_OUT * TP;
+    s.wt1 = p; p += D_IN * D_H; s.b1 = p; p += D_H;
+    s.wt2 = p; p += D_H * D_H; s.b2 = p; p += D_H;
+    s.w3t = p; p += D_H * D_OUT; s.b3 = p; p += D_OUT;
+    if (bwd) { s.w1 = p; p += D_H * D_IN; s.w2 = p; p += D_H * D_H; s.w3 = p; p += D_OUT * D_H; }
+    else { s.w1 = s.w2 = s.w3 = nullptr; }
+    s.lv = reinterpret_cast<LevelSm*>(p);
+    return s;
+}
+
+constexpr size_t smem_bytes(bool bwd) {
+    return sizeof(float) * ((D_IN + 2 * D_H + D_OUT) * TP + D_IN * D_H + D_H + D_H * D_H + D_H + D_H * D_OUT + D_OUT
+                            + (bwd ? (D_H * D_IN + D_H * D_H + D_OUT * D_H) : 0)) + 16 * sizeof(LevelSm);
+}
+
+__device__ __forceinline__ void load_weights(const Smem& s, const mi3d_mlp& m, const mi3d_hashgrid& hg, bool bwd) {
+    for (int i = threadIdx.x; i < D_H * D_IN; i += NT) {           // W1 [64][32]
+        const int j = i / D_IN, k = i % D_IN; const float v = m.w1[i];
+        s.wt1[k * D_H + j] = v; if (bwd) s.w1[i] = v;
+    }
+    for (int i = threadIdx.x; i < D_H * D_H; i += NT) {            // W2 [64][64]
+        const int j = i / D_H, k = i % D_H; const float v = m.w2[i];
+        s.wt2[k * D_H + j] = v; if (bwd) s.w2[i] = v;
+    }
+    for (int i = threadIdx.x; i < D_OUT * D_H; i += NT) {          // W3 [4][64]
+        const int j = i / D_H, k = i % D_H; const float v = m.w3[i];
+        s.w3t[k * D_OUT + j] = v; if (bwd) s.w3[i] = v;
+    }
+    for (int i = threadIdx.x; i < D_H; i += NT) { s.b1[i] = m.b1[i]; s.b2[i] = m.b2[i]; }
+    if (threadIdx.x < D_OUT) s.b3[threadIdx.x] = m.b3[threadIdx.x];
+    if (threadIdx.x < 16) {
+        LevelSm L; const int l = threadIdx.x;
+        if (l < (int)hg.n_levels) {
+            L.offset = hg.offsets[l]; L.size = hg.sizes[l]; L.res = hg.ress[l]; L.scale = hg.scales[l];
+            const uint64_t dense = (uint64_t)L.res * L.res * L.res;
+            L.hashed = dense > (uint64_t)L.size ? 1u : 0u;
+        } else { L.offset = 0; L.size = 8; L.res = 2; L.scale = 1.f; L.hashed = 0; }
+        s.lv[l] = L;
+    }
+}
+
+__device__ __forceinline__ uint32_t padded_rows(uint32_t M, uint32_t align, uint32_t cap) {
+    uint32_t m = M;
+    if (align > 0) m += align - m % align;        // raymarching.py:238-239 (always adds, even when already aligned)
+    return m < cap ? m : cap;
+}
+
+// position of evaluation e for a sample at x (perturbation pz = x + 0.01*noise for e >= 7)
+__device__ __forceinline__ void eval_pos(int e, const float x[3], const float xp[3], float bound, float p[3]) {
+    const float* base = e >= 7 ? xp : x;
+    p[0] = base[0]; p[1] = base[1]; p[2] = base[2];
+    if (e > 0) {
+        const int t = (e - 1) % 6, axis = t >> 1;
+        const float sgn = (t & 1) ? -kFdEps : kFdEps;
+        // the reference clamps all three coordinates of the tap position (network_tcnn.py:117-122)
+        #pragma unroll
+        for (int d = 0; d < 3; d++) p[d] = mi3d_clampf(d == axis ? p[d] + sgn : p[d], -bound, bound);
+    }
+}
+
+__device__ __forceinline__ float blob(const float p[3], float density, float two_r2) {
+    const float d = (p[0] * p[0] + p[1] * p[1]) + p[2] * p[2];
+    return density * expf(-d / two_r2);
+}
+
+__device__ __forceinline__ float nan_to_num(float v) {
+    if (isnan(v)) return 0.f;
+    if (isinf(v)) return v > 0 ? FLT_MAX : -FLT_MAX;
+    return v;
+}
+
+struct Normal { float g[3]; float q; float inv; float n[3]; bool finite[3]; bool in_clamp; };
+
+__device__ __forceinline__ Normal make_normal(const float sp[3], const float sn[3]) {
+    Normal r;
+    #pragma unroll
+    for (int a = 0; a < 3; a++) r.g[a] = -(0.5f * (sp[a] - sn[a]) / kFdEps);
+    const float S = (r.g[0] * r.g[0] + r.g[1] * r.g[1]) + r.g[2] * r.g[2];
+    r.in_clamp = (S >= 1e-20f) && (S <= 1e32f);
+    r.q = fminf(fmaxf(S, 1e-20f), 1e32f);
+    if (isnan(S)) r.q = S;
+    const float rt = sqrtf(r.q);
+    #pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float v = r.g[a] / rt;
+        r.finite[a] = isfinite(v);
+        r.n[a] = nan_to_num(v);
+    }
+    r.inv = 1.f / rt;
+    return r;
+}
+
+// d(loss)/dg given d(loss)/dn, through nan_to_num and safe_normalize
+__device__ __forceinline__ void normal_bwd(const Normal& nm, const float dn_in[3], float dg[3]) {
+    float dn[3];
+    #pragma unroll
+    for (int a = 0; a < 3; a++) dn[a] = nm.finite[a] ? dn_in[a] : 0.f;
+    // n = g * q^-1/2 ; dq = -0.5 q^-3/2 sum(dn*g)
+    const float dot = (dn[0] * nm.g[0] + dn[1] * nm.g[1]) + dn[2] * nm.g[2];
+    const float dq = -0.5f * dot * nm.inv * nm.inv * nm.inv;
+    const float dS = nm.in_clamp ? dq : 0.f;
+    #pragma unroll
+    for (int a = 0; a < 3; a++) dg[a] = dn[a] * nm.inv + 2.f * dS * nm.g[a];
+}
+
+__device__ __forceinline__ void gauss_pair(uint64_t seed, uint32_t row, uint32_t salt, float out[3]) {
+    const uint4 r = mi3d_philox(make_uint4(row, salt, 0u, 0x736d6f6fu), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u1 = fmaxf(mi3d_u01(r.x), 5.9604645e-8f), u2 = mi3d_u01(r.y), u3 = fmaxf(mi3d_u01(r.z), 5.9604645e-8f), u4 = mi3d_u01(r.w);
+    const float m1 = sqrtf(-2.f * logf(u1)), m2 = sqrtf(-2.f * logf(u3));
+    out[0] = m1 * cospif(2.f * u2); out[1] = m1 * sinpif(2.f * u2); out[2] = m2 * cospif(2.f * u4);
+}
+
+struct FwdArgs {
+    const float* xyzs; const float* dirs; const int* counter; uint32_t m_fixed, align, cap;
+    const float* table; mi3d_hashgrid hg; mi3d_mlp mlp;
+    float bound, blob_density, two_r2;
+    int n_evals, shading; float ratio; const float* light_d;
+    const float* smooth_noise; uint64_t seed;
+    float* sigmas; float* rgbs; float* normals; float* tape; float* loss_partials;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 2) k_field_fwd(const FwdArgs a) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, false);
+    load_weights(s, a.mlp, a.hg, false);
+    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
+    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
+    const int lrow = threadIdx.x & (T - 1), half = threadIdx.x >> 7;
+    const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
+    const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;   // network_tcnn.py:159 fallback
+    float light[3] = {0.f, 0.f, 0.f};
+    if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
+    float acc_orient = 0.f, acc_smooth = 0.f;
+    __syncthreads();
+
+    for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+        const uint32_t row = tile * T + lrow;
+        const bool in_range = row < m_pad, real = row < M;
+        float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
+        if (real) {
+            x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2];
+            if (a.dirs) { d[0] = a.dirs[3 * (size_t)row]; d[1] = a.dirs[3 * (size_t)row + 1]; d[2] = a.dirs[3 * (size_t)row + 2]; }
+        }
+        if (a.n_evals > 7 && in_range) {
+            float z[3];
+            if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
+            else gauss_pair(a.seed, row, 1u, z);
+            #pragma unroll
+            for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
+        }
+        float sigma0 = 0.f, alb[3] = {0.f, 0.f, 0.f}, tapv[12];
+        #pragma unroll
+        for (int i = 0; i < 12; i++) tapv[i] = 0.f;
+
+        for (int e = 0; e < a.n_evals; e++) {
+            float p[3];
+            eval_pos(e, x, xp, a.bound, p);
+            const float inv2b = 2.f * a.bound;
+            encode_levels(a.table, s.lv, l0, lcount, (p[0] + a.bound) / inv2b, (p[1] + a.bound) / inv2b, (p[2] + a.bound) / inv2b,
+                          s.enc, TP, lrow);
+            __syncthreads();
+            tile_gemm<D_IN, D_H, true, false>(s.enc, s.wt1, s.b1, s.h1, nullptr);
+            __syncthreads();
+            tile_gemm<D_H, D_H, true, false>(s.h1, s.wt2, s.b2, s.h2, nullptr);
+            __syncthreads();
+            out_layer(s.h2, s.w3t, s.b3, s.o);
+            __syncthreads();
+            if (half == 0) {
+                const float sg = expf(s.o[lrow] + blob(p, a.blob_density, a.two_r2));
+                if (e == 0) {
+                    sigma0 = sg;
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++) alb[c] = 1.f / (1.f + expf(-s.o[(1 + c) * TP + lrow]));
+                } else {
+                    #pragma unroll
+                    for (int i = 0; i < 12; i++) if (i == e - 1) tapv[i] = sg;
+                }
+            }
+        }
+        if (half == 0 && in_range) {
+            float col[3] = {alb[0], alb[1], alb[2]};
+            Normal nm, np;
+            if (a.n_evals >= 7) {
+                const float sp[3] = {tapv[0], tapv[2], tapv[4]}, sn[3] = {tapv[1], tapv[3], tapv[5]};
+                nm = make_normal(sp, sn);
+                if (lit) {
+                    const float ndl = (nm.n[0] * light[0] + nm.n[1] * light[1]) + nm.n[2] * light[2];
+                    const float lam = a.ratio + (1 - a.ratio) * fmaxf(ndl, 0.1f);
+                    if (a.shading == MI3D_SHADING_TEXTURELESS) { col[0] = col[1] = col[2] = lam; }
+                    else if (a.shading == MI3D_SHADING_NORMAL) { col[0] = (nm.n[0] + 1) / 2; col[1] = (nm.n[1] + 1) / 2; col[2] = (nm.n[2] + 1) / 2; }
+                    else { col[0] = alb[0] * lam; col[1] = alb[1] * lam; col[2] = alb[2] * lam; }
+                }
+                const float wgt = 1.f - expf(-sigma0);
+                const float ndd = fmaxf((nm.n[0] * d[0] + nm.n[1] * d[1]) + nm.n[2] * d[2], 0.f);
+                acc_orient += wgt * (ndd * ndd);
+                if (a.n_evals > 7) {
+                    const float sp2[3] = {tapv[6], tapv[8], tapv[10]}, sn2[3] = {tapv[7], tapv[9], tapv[11]};
+                    np = make_normal(sp2, sn2);
+                    acc_smooth += (fabsf(nm.n[0] - np.n[0]) + fabsf(nm.n[1] - np.n[1])) + fabsf(nm.n[2] - np.n[2]);
+                }
+                if (a.normals) { a.normals[3 * (size_t)row] = nm.n[0]; a.normals[3 * (size_t)row + 1] = nm.n[1]; a.normals[3 * (size_t)row + 2] = nm.n[2]; }
+            }
+            a.sigmas[row] = sigma0;
+            if (a.rgbs) { a.rgbs[3 * (size_t)row] = col[0]; a.rgbs[3 * (size_t)row + 1] = col[1]; a.rgbs[3 * (size_t)row + 2] = col[2]; }
+            if (a.tape) {
+                float4* tp = reinterpret_cast<float4*>(a.tape + 16 * (size_t)row);
+                tp[0] = make_float4(sigma0, alb[0], alb[1], alb[2]);
+                tp[1] = make_float4(tapv[0], tapv[1], tapv[2], tapv[3]);
+                tp[2] = make_float4(tapv[4], tapv[5], tapv[6], tapv[7]);
+                tp[3] = make_float4(tapv[8], tapv[9], tapv[10], tapv[11]);
+            }
+        }
+    }
+    if (a.loss_partials) {
+        // deterministic block reduction (fixed order), one slot per CTA
+        __shared__ float red[2][NT / 32];
+        float v0 = acc_orient, v1 = acc_smooth;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = v0; red[1][threadIdx.x >> 5] = v1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t0 = 0.f, t1 = 0.f;
+            for (int w = 0; w < NT / 32; w++) { t0 += red[0][w]; t1 += red[1][w]; }
+            a.loss_partials[2 * blockIdx.x] = t0; a.loss_partials[2 * blockIdx.x + 1] = t1;
+        }
+    }
+}
+
+// loss_orient = sum / m_pad ; loss_smooth = sum / (3 m_pad)   (renderer.py:517-518, 523-524: .mean() over the padded rows)
+__global__ void k_loss_finalize(const float* __restrict__ partials, int n_part, const int* __restrict__ counter, uint32_t m_fixed,
+                                uint32_t align, uint32_t cap, float* __restrict__ loss_orient, float* __restrict__ loss_smooth) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float t0 = 0.f, t1 = 0.f;
+    for (int i = 0; i < n_part; i++) { t0 += partials[2 * i]; t1 += partials[2 * i + 1]; }
+    const uint32_t M = counter ? min((uint32_t)counter[0], cap) : m_fixed;
+    const float m_pad = (float)padded_rows(M, align, cap);
+    if (loss_orient) *loss_orient = t0 / m_pad;
+    if (loss_smooth) *loss_smooth = t1 / (3.f * m_pad);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+struct BwdArgs {
+    const float* xyzs; const float* dirs; const int* counter; uint32_t m_fixed, align, cap;
+    const float* table; mi3d_hashgrid hg; mi3d_mlp mlp;
+    float bound, blob_density, two_r2;
+    int n_evals, shading; float ratio; const float* light_d;
+    const float* smooth_noise; uint64_t seed;
+    const float* tape;
+    const float* g_sigmas; const float* g_rgbs; const float* g_normals; const float* g_loss_orient; const float* g_loss_smooth;
+    float* g_table; mi3d_mlp_grad g_mlp;
+};
+
+__global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, true);
+    load_weights(s, a.mlp, a.hg, true);
+    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
+    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
+    const int lrow = threadIdx.x & (T - 1), half = threadIdx.x >> 7;
+    const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
+    const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
+    float light[3] = {0.f, 0.f, 0.f};
+    if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
+    const float Go = (a.g_loss_orient && a.n_evals >= 7) ? *a.g_loss_orient / (float)m_pad : 0.f;
+    const float Gs = (a.g_loss_smooth && a.n_evals > 7) ? *a.g_loss_smooth / (3.f * (float)m_pad) : 0.f;
+    // which evaluations can receive a non-zero gradient (CTA-uniform)
+    const bool need_ptaps = Gs != 0.f;
+    const bool need_taps = a.n_evals >= 7 && (need_ptaps || Go != 0.f || lit || a.g_normals != nullptr);
+    const int e_end = !need_taps ? 1 : (need_ptaps ? 13 : 7);
+
+    float aw2[4][4], aw1[4][2], aw3 = 0.f, ab2[4], ab1[4], ab3 = 0.f;
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ab2[i] = 0.f; ab1[i] = 0.f;
+        #pragma unroll
+        for (int j = 0; j < 4; j++) aw2[i][j] = 0.f;
+        aw1[i][0] = 0.f; aw1[i][1] = 0.f;
+    }
+    __syncthreads();
+
+    for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+        const uint32_t row = tile * T + lrow;
+        const bool in_range = row < m_pad, real = row < M;
+        float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
+        if (real) {
+            x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2];
+            if (a.dirs) { d[0] = a.dirs[3 * (size_t)row]; d[1] = a.dirs[3 * (size_t)row + 1]; d[2] = a.dirs[3 * (size_t)row + 2]; }
+        }
+        if (a.n_evals > 7 && in_range) {
+            float z[3];
+            if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
+            else gauss_pair(a.seed, row, 1u, z);
+            #pragma unroll
+            for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
+        }
+        // ---- per-sample output gradients (threads of half 0 own a sample) ----
+        float dh[4] = {0.f, 0.f, 0.f, 0.f};     // d/d(h0..h3) of the centre evaluation
+        float dtap[12];                          // d/d(h0) of the 12 tap evaluations
+        #pragma unroll
+        for (int i = 0; i < 12; i++) dtap[i] = 0.f;
+        if (half == 0 && in_range) {
+            const float4* tp = reinterpret_cast<const float4*>(a.tape + 16 * (size_t)row);
+            const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
+            const float sigma0 = t0.x, alb[3] = {t0.y, t0.z, t0.w};
+            const float tapv[12] = {t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t3.x, t3.y, t3.z, t3.w};
+            float gs = 0.f, gc[3] = {0.f, 0.f, 0.f};
+            if (real) {
+                if (a.g_sigmas) gs = a.g_sigmas[row];
+                if (a.g_rgbs) { gc[0] = a.g_rgbs[3 * (size_t)row]; gc[1] = a.g_rgbs[3 * (size_t)row + 1]; gc[2] = a.g_rgbs[3 * (size_t)row + 2]; }
+            }
+            float dalb[3] = {gc[0], gc[1], gc[2]};
+            float dn[3] = {0.f, 0.f, 0.f}, dnp[3] = {0.f, 0.f, 0.f};
+            if (a.n_evals >= 7) {
+                const float sp[3] = {tapv[0], tapv[2], tapv[4]}, sn[3] = {tapv[1], tapv[3], tapv[5]};
+                const Normal nm = make_normal(sp, sn);
+                if (a.g_normals && real) { dn[0] += a.g_normals[3 * (size_t)row]; dn[1] += a.g_normals[3 * (size_t)row + 1]; dn[2] += a.g_normals[3 * (size_t)row + 2]; }
+                if (lit) {
+                    const float ndl = (nm.n[0] * light[0] + nm.n[1] * light[1]) + nm.n[2] * light[2];
+                    const float lam = a.ratio + (1 - a.ratio) * fmaxf(ndl, 0.1f);
+                    float dlam = 0.f;
+                    if (a.shading == MI3D_SHADING_TEXTURELESS) { dlam = (gc[0] + gc[1]) + gc[2]; dalb[0] = dalb[1] = dalb[2] = 0.f; }
+                    else if (a.shading == MI3D_SHADING_NORMAL) { dn[0] += 0.5f * gc[0]; dn[1] += 0.5f * gc[1]; dn[2] += 0.5f * gc[2]; dalb[0] = dalb[1] = dalb[2] = 0.f; }
+                    else { dlam = (gc[0] * alb[0] + gc[1] * alb[1]) + gc[2] * alb[2]; dalb[0] = gc[0] * lam; dalb[1] = gc[1] * lam; dalb[2] = gc[2] * lam; }
+                    if (ndl >= 0.1f) {
+                        const float k = dlam * (1 - a.ratio);
+                        dn[0] += k * light[0]; dn[1] += k * light[1]; dn[2] += k * light[2];
+                    }
+                }
+                if (Go != 0.f) {
+                    const float wgt = 1.f - expf(-sigma0);
+                    const float ndd = (nm.n[0] * d[0] + nm.n[1] * d[1]) + nm.n[2] * d[2];
+                    if (ndd > 0.f) { const float k = Go * wgt * 2.f * ndd; dn[0] += k * d[0]; dn[1] += k * d[1]; dn[2] += k * d[2]; }
+                }
+                Normal np;
+                if (need_ptaps) {
+                    const float sp2[3] = {tapv[6], tapv[8], tapv[10]}, sn2[3] = {tapv[7], tapv[9], tapv[11]};
+                    np = make_normal(sp2, sn2);
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float df = nm.n[c] - np.n[c];
+                        const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+                        dn[c] += Gs * sg; dnp[c] -= Gs * sg;
+                    }
+                }
+                float dg[3];
+                normal_bwd(nm, dn, dg);
+                #pragma unroll
+                for (int ax = 0; ax < 3; ax++) {
+                    // g = -(0.5 (s+ - s-) / eps)  ->  ds+ = -0.5/eps dg ; ds- = +0.5/eps dg ; dh0 = ds * exp(min(h,15)) = ds * min(s, e^15)
+                    const float k = 0.5f / kFdEps * dg[ax];
+                    dtap[2 * ax] = -k * fminf(tapv[2 * ax], 3269017.372472110639f);
+                    dtap[2 * ax + 1] = k * fminf(tapv[2 * ax + 1], 3269017.372472110639f);
+                }
+                if (need_ptaps) {
+                    normal_bwd(np, dnp, dg);
+                    #pragma unroll
+                    for (int ax = 0; ax < 3; ax++) {
+                        const float k = 0.5f / kFdEps * dg[ax];
+                        dtap[6 + 2 * ax] = -k * fminf(tapv[6 + 2 * ax], 3269017.372472110639f);
+                        dtap[6 + 2 * ax + 1] = k * fminf(tapv[6 + 2 * ax + 1], 3269017.372472110639f);
+                    }
+                }
+            }
+            dh[0] = gs * fminf(sigma0, 3269017.372472110639f);       // activation.py:12-16
+            #pragma unroll
+            for (int c = 0; c < 3; c++) dh[1 + c] = dalb[c] * alb[c] * (1.f - alb[c]);
+        }
+
+        for (int e = 0; e < e_end; e++) {
+            float p[3];
+            eval_pos(e, x, xp, a.bound, p);
+            const float inv2b = 2.f * a.bound;
+            const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
+            encode_levels(a.table, s.lv, l0, lcount, u0, u1, u2, s.enc, TP, lrow);
+            if (half == 0) {
+                float g0 = 0.f;
+                if (e == 0) { g0 = dh[0]; s.o[1 * TP + lrow] = dh[1]; s.o[2 * TP + lrow] = dh[2]; s.o[3 * TP + lrow] = dh[3]; }
+                else {
+                    #pragma unroll
+                    for (int i = 0; i < 12; i++) if (i == e - 1) g0 = dtap[i];
+                    s.o[1 * TP + lrow] = 0.f; s.o[2 * TP + lrow] = 0.f; s.o[3 * TP + lrow] = 0.f;
+                }
+                s.o[lrow] = g0;
+            }
+            __syncthreads();
+            tile_gemm<D_IN, D_H, true, false>(s.enc, s.wt1, s.b1, s.h1, nullptr);
+            __syncthreads();
+            tile_gemm<D_H, D_H, true, false>(s.h1, s.wt2, s.b2, s.h2, nullptr);
+            __syncthreads();
+            // layer 3: dW3 += dO^T H2 ; dH2 = relu'(H2) * (dO W3)
+            tile_wgrad3(s.o, s.h2, aw3, ab3);
+            __syncthreads();
+            tile_gemm<D_OUT, D_H, false, true>(s.o, s.w3, nullptr, s.h2, s.h2);
+            __syncthreads();
+            // layer 2
+            tile_wgrad<4>(s.h2, s.h1, aw2, ab2);
+            __syncthreads();
+            tile_gemm<D_H, D_H, false, true>(s.h2, s.w2, nullptr, s.h1, s.h1);
+            __syncthreads();
+            // layer 1
+            tile_wgrad<2>(s.h1, s.enc, aw1, ab1);
+            __syncthreads();
+            tile_gemm<D_H, D_IN, false, false>(s.h1, s.w1, nullptr, s.enc, nullptr);
+            __syncthreads();
+            if (in_range) scatter_levels(a.g_table, s.lv, l0, lcount, u0, u1, u2, s.enc, TP, lrow);
+            __syncthreads();
+        }
+    }
+    // flush the register-resident weight gradients (one RED per element per CTA)
+    {
+        const int jt = threadIdx.x >> 4, it = threadIdx.x & 15;
+        #pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int j = jt + 16 * p;
+            #pragma unroll
+            for (int q = 0; q < 4; q++) atomicAdd(a.g_mlp.w2 + j * D_H + it + 16 * q, aw2[p][q]);
+            #pragma unroll
+            for (int q = 0; q < 2; q++) atomicAdd(a.g_mlp.w1 + j * D_IN + it + 16 * q, aw1[p][q]);
+            if (it == 0) { atomicAdd(a.g_mlp.b2 + j, ab2[p]); atomicAdd(a.g_mlp.b1 + j, ab1[p]); }
+        }
+        const int o = threadIdx.x >> 6, i = threadIdx.x & 63;
+        atomicAdd(a.g_mlp.w3 + o * D_H + i, aw3);
+        if (i == 0) atomicAdd(a.g_mlp.b3 + o, ab3);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stand-alone hash-grid encoder (tcnn.Encoding drop-in used by the unfused B2 path and by parity tests)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_hashgrid_fwd(const float* __restrict__ x, uint32_t E, const float* __restrict__ table, const mi3d_hashgrid hg,
+                               float* __restrict__ out) {
+    __shared__ LevelSm lv[16];
+    if (threadIdx.x < 16) {
+        LevelSm L; const int l = threadIdx.x;
+        if (l < (int)hg.n_levels) {
+            L.offset = hg.offsets[l]; L.size = hg.sizes[l]; L.res = hg.ress[l]; L.scale = hg.scales[l];
+            L.hashed = (uint64_t)L.res * L.res * L.res > (uint64_t)L.size ? 1u : 0u;
+        } else { L.offset = 0; L.size = 8; L.res = 2; L.scale = 1.f; L.hashed = 0; }
+        lv[l] = L;
+    }
+    __syncthreads();
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int nl = (int)hg.n_levels;
+    encode_levels(table, lv, 0, nl, x[3 * (size_t)e], x[3 * (size_t)e + 1], x[3 * (size_t)e + 2], out + (size_t)e * 2 * nl, 1, 0);
+}
+
+__global__ void k_hashgrid_bwd(const float* __restrict__ x, uint32_t E, const float* __restrict__ g_out, const mi3d_hashgrid hg,
+                               float* __restrict__ g_table) {
+    __shared__ LevelSm lv[16];
+    if (threadIdx.x < 16) {
+        LevelSm L; const int l = threadIdx.x;
+        if (l < (int)hg.n_levels) {
+            L.offset = hg.offsets[l]; L.size = hg.sizes[l]; L.res = hg.ress[l]; L.scale = hg.scales[l];
+            L.hashed = (uint64_t)L.res * L.res * L.res > (uint64_t)L.size ? 1u : 0u;
+        } else { L.offset = 0; L.size = 8; L.res = 2; L.scale = 1.f; L.hashed = 0; }
+        lv[l] = L;
+    }
+    __syncthreads();
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int nl = (int)hg.n_levels;
+    scatter_levels(g_table, lv, 0, nl, x[3 * (size_t)e], x[3 * (size_t)e + 1], x[3 * (size_t)e + 2], g_out + (size_t)e * 2 * nl, 1, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// density-grid refresh (nerf/renderer.py:587-637): cell centres + jitter, EMA-max, mean, threshold
+// ---------------------------------------------------------------------------------------------------------
+// positions for cascade `cas`, Morton-ordered: cell index m -> coords (morton inverse) -> xyz
+__global__ void k_grid_positions(uint32_t H, float cas_bound, const float* __restrict__ jitter, uint64_t seed, uint32_t cas,
+                                 float* __restrict__ xyz) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = H * H * H;
+    if (m >= n) return;
+    const float half_grid = cas_bound / (float)H;
+    const uint32_t c[3] = {mi3d_compact3(m), mi3d_compact3(m >> 1), mi3d_compact3(m >> 2)};
+    float u[3];
+    if (jitter) { u[0] = jitter[3 * (size_t)m]; u[1] = jitter[3 * (size_t)m + 1]; u[2] = jitter[3 * (size_t)m + 2]; }
+    else {
+        const uint4 r = mi3d_philox(make_uint4(m, cas, 0u, 0x67726964u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        u[0] = mi3d_u01(r.x); u[1] = mi3d_u01(r.y); u[2] = mi3d_u01(r.z);
+    }
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float base = 2.f * (float)c[d] / (float)(H - 1) - 1.f;           // renderer.py:608
+        float v = base * (cas_bound - half_grid);                              // :615
+        v += (u[d] * 2.f - 1.f) * half_grid;                                   // :617
+        xyz[3 * (size_t)m + d] = v;
+    }
+}
+
+// grid[cas][m] = max(grid*decay, sigma) where grid >= 0 ; block partial sums of the valid cells for the mean
+__global__ void k_grid_ema(float* __restrict__ grid, const float* __restrict__ sigmas, uint32_t n, float decay,
+                           float* __restrict__ partial_sum, uint32_t* __restrict__ partial_cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float v = 0.f; uint32_t c = 0;
+    if (i < n) {
+        float g = grid[i];
+        if (g >= 0.f) { g = fmaxf(g * decay, sigmas[i]); grid[i] = g; v = g; c = 1; }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    __shared__ float sv[8]; __shared__ uint32_t sc[8];
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; sc[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tv = 0.f; uint32_t tc = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { tv += sv[w]; tc += sc[w]; }
+        partial_sum[blockIdx.x] = tv; partial_cnt[blockIdx.x] = tc;
+    }
+}
+
+__global__ void k_grid_mean(const float* __restrict__ partial_sum, const uint32_t* __restrict__ partial_cnt, uint32_t nparts,
+                            float* __restrict__ mean_out) {
+    __shared__ double sv[256]; __shared__ unsigned long long sc[256];
+    double v = 0; unsigned long long c = 0;
+    for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) { v += (double)partial_sum[i]; c += partial_cnt[i]; }
+    sv[threadIdx.x] = v; sc[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) { sv[threadIdx.x] += sv[threadIdx.x + o]; sc[threadIdx.x] += sc[threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) *mean_out = sc[0] ? (float)(sv[0] / (double)sc[0]) : 0.f;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+bool g_attr_set = false;
+int ensure_attrs() {
+    if (!g_attr_set) {
+        MI3D_CHECK(cudaFuncSetAttribute(k_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false)));
+        MI3D_CHECK(cudaFuncSetAttribute(k_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true)));
+        g_attr_set = true;
+    }
+    return MI3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mi3d_hashgrid_make(uint32_t n_levels, uint32_t base_resolution, double per_level_scale, uint32_t log2_hashmap_size, mi3d_hashgrid* out) {
+    if (!out || n_levels == 0 || n_levels > 16 || log2_hashmap_size > 28) return MI3D_ERR_ARG;
+    uint32_t off = 0;
+    const uint64_t cap = (uint64_t)1 << log2_hashmap_size;
+    for (uint32_t l = 0; l < 16; l++) { out->offsets[l] = 0; out->sizes[l] = 0; out->ress[l] = 0; out->scales[l] = 0.f; }
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const float scale = exp2f((float)l * log2f((float)per_level_scale)) * (float)base_resolution - 1.0f;
+        const uint32_t res = (uint32_t)ceilf(scale) + 1;
+        const uint64_t dense = (uint64_t)res * res * res;
+        uint64_t size = dense < cap ? dense : cap;
+        size = (size + 7) / 8 * 8;
+        if (size > cap) size = cap;
+        out->offsets[l] = off; out->sizes[l] = (uint32_t)size; out->ress[l] = res; out->scales[l] = scale;
+        off += (uint32_t)size;
+    }
+    out->n_levels = n_levels;
+    out->n_entries = off;
+    return MI3D_OK;
+}
+
+int mi3d_hashgrid_forward(const float* x, uint32_t E, const float* table, const mi3d_hashgrid* hg, float* out, mi3d_stream_t stream) {
+    if (E == 0) return MI3D_OK;
+    if (!hg) return MI3D_ERR_ARG;
+    k_hashgrid_fwd<<<mi3d_ceil_div(E, 128), 128, 0, (cudaStream_t)stream>>>(x, E, table, *hg, out);
+    MI3D_RETURN_LAUNCH();
+}
+
+int mi3d_hashgrid_backward(const float* x, uint32_t E, const float* grad_out, const mi3d_hashgrid* hg, float* grad_table, mi3d_stream_t stream) {
+    if (E == 0) return MI3D_OK;
+    if (!hg) return MI3D_ERR_ARG;
+    k_hashgrid_bwd<<<mi3d_ceil_div(E, 128), 128, 0, (cudaStream_t)stream>>>(x, E, grad_out, *hg, grad_table);
+    MI3D_RETURN_LAUNCH();
+}
+
+int mi3d_field_grid_ctas(int backward) { return num_sms() * (backward ? 1 : 2); }
+
+int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
+                       const mi3d_field_cfg* cfg, float* sigmas, float* rgbs, float* normals, float* tape,
+                       float* loss_partials, float* loss_orient, float* loss_smooth, mi3d_stream_t stream) {
+    if (!io || !hg || !mlp || !cfg || !sigmas) return MI3D_ERR_ARG;
+    if (cfg->n_evals != 1 && cfg->n_evals != 7 && cfg->n_evals != 13) return MI3D_ERR_ARG;
+    if (hg->n_levels * 2 != D_IN) return MI3D_ERR_ARG;
+    if ((loss_orient || loss_smooth) && !loss_partials) return MI3D_ERR_ARG;
+    MI3D_CHECK((cudaError_t)ensure_attrs());
+    FwdArgs a;
+    a.xyzs = io->xyzs; a.dirs = io->dirs; a.counter = io->counter; a.m_fixed = io->m_fixed; a.align = io->align; a.cap = io->cap;
+    a.table = table; a.hg = *hg; a.mlp = *mlp;
+    a.bound = cfg->bound; a.blob_density = cfg->blob_density; a.two_r2 = (float)(2.0 * (double)cfg->blob_radius * (double)cfg->blob_radius);
+    a.n_evals = cfg->n_evals; a.shading = cfg->shading; a.ratio = cfg->ambient_ratio; a.light_d = cfg->light_d;
+    a.smooth_noise = io->smooth_noise; a.seed = io->seed;
+    a.sigmas = sigmas; a.rgbs = rgbs; a.normals = normals; a.tape = tape; a.loss_partials = loss_partials;
+    const int grid = mi3d_field_grid_ctas(0);
+    k_field_fwd<<<grid, NT, smem_bytes(false), (cudaStream_t)stream>>>(a);
+    if (loss_orient || loss_smooth)
+        k_loss_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partials, grid, io->counter, io->m_fixed, io->align, io->cap, loss_orient, loss_smooth);
+    MI3D_RETURN_LAUNCH();
+}
+
+int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
+                        const mi3d_field_cfg* cfg, const float* tape, const float* grad_sigmas, const float* grad_rgbs,
+                        const float* grad_normals, const float* grad_loss_orient, const float* grad_loss_smooth,
+                        float* grad_table, const mi3d_mlp_grad* grad_mlp, mi3d_stream_t stream) {
+    if (!io || !hg || !mlp || !cfg || !tape || !grad_table || !grad_mlp) return MI3D_ERR_ARG;
+    if (cfg->n_evals != 1 && cfg->n_evals != 7 && cfg->n_evals != 13) return MI3D_ERR_ARG;
+    if (hg->n_levels * 2 != D_IN) return MI3D_ERR_ARG;
+    MI3D_CHECK((cudaError_t)ensure_attrs());
+    BwdArgs a;
+    a.xyzs = io->xyzs; a.dirs = io->dirs; a.counter = io->counter; a.m_fixed = io->m_fixed; a.align = io->align; a.cap = io->cap;
+    a.table = table; a.hg = *hg; a.mlp = *mlp;
+    a.bound = cfg->bound; a.blob_density = cfg->blob_density; a.two_r2 = (float)(2.0 * (double)cfg->blob_radius * (double)cfg->blob_radius);
+    a.n_evals = cfg->n_evals; a.shading = cfg->shading; a.ratio = cfg->ambient_ratio; a.light_d = cfg->light_d;
+    a.smooth_noise = io->smooth_noise; a.seed = io->seed;
+    a.tape = tape; a.g_sigmas = grad_sigmas; a.g_rgbs = grad_rgbs; a.g_normals = grad_normals;
+    a.g_loss_orient = grad_loss_orient; a.g_loss_smooth = grad_loss_smooth;
+    a.g_table = grad_table; a.g_mlp = *grad_mlp;
+    k_field_bwd<<<mi3d_field_grid_ctas(1), NT, smem_bytes(true), (cudaStream_t)stream>>>(a);
+    MI3D_RETURN_LAUNCH();
+}
+
+size_t mi3d_density_grid_workspace_bytes(uint32_t C, uint32_t H) {
+    const size_t n = (size_t)H * H * H;
+    const size_t nparts = (n + 255) / 256;
+    return n * 3 * sizeof(float) + n * sizeof(float) + (size_t)C * nparts * (sizeof(float) + sizeof(uint32_t)) + 256;
+}
+
+// nerf/renderer.py:587-637 without the two .item() host syncs: the mean density and the packing threshold
+// min(mean, density_thresh) stay on the device (mean_density_out is a device scalar the caller may read later).
+int mi3d_density_grid_update(float* density_grid, uint8_t* bitfield, uint32_t C, uint32_t H, float bound, float decay,
+                             float density_thresh, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
+                             const mi3d_field_cfg* cfg, const float* jitter, uint64_t seed, float* mean_density_out,
+                             void* workspace, mi3d_stream_t stream) {
+    if (!density_grid || !bitfield || !hg || !mlp || !cfg || !workspace || !mean_density_out || C == 0 || C > 8) return MI3D_ERR_ARG;
+    if (hg->n_levels * 2 != D_IN) return MI3D_ERR_ARG;
+    MI3D_CHECK((cudaError_t)ensure_attrs());
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t n = H * H * H;
+    const uint32_t nparts = mi3d_ceil_div(n, 256);
+    float* xyz = (float*)workspace;
+    float* sig = xyz + (size_t)n * 3;
+    float* psum = sig + n;
+    uint32_t* pcnt = (uint32_t*)(psum + (size_t)nparts * C);
+    for (uint32_t cas = 0; cas < C; cas++) {
+        const float cas_bound = fminf((float)(1u << cas), bound);                 // renderer.py:612
+        k_grid_positions<<<nparts, 256, 0, st>>>(H, cas_bound, jitter ? jitter + (size_t)cas * n * 3 : nullptr, seed, cas, xyz);
+        FwdArgs a;
+        a.xyzs = xyz; a.dirs = nullptr; a.counter = nullptr; a.m_fixed = n; a.align = 0; a.cap = n;
+        a.table = table; a.hg = *hg; a.mlp = *mlp;
+        a.bound = cfg->bound; a.blob_density = cfg->blob_density; a.two_r2 = (float)(2.0 * (double)cfg->blob_radius * (double)cfg->blob_radius);
+        a.n_evals = 1; a.shading = MI3D_SHADING_ALBEDO; a.ratio = 1.f; a.light_d = nullptr;
+        a.smooth_noise = nullptr; a.seed = 0;
+        a.sigmas = sig; a.rgbs = nullptr; a.normals = nullptr; a.tape = nullptr; a.loss_partials = nullptr;
+        k_field_fwd<<<mi3d_field_grid_ctas(0), NT, smem_bytes(false), st>>>(a);
+        k_grid_ema<<<nparts, 256, 0, st>>>(density_grid + (size_t)cas * n, sig, n, decay, psum + (size_t)cas * nparts, pcnt + (size_t)cas * nparts);
+    }
+    k_grid_mean<<<1, 256, 0, st>>>(psum, pcnt, nparts * C, mean_density_out);
+    MI3D_CHECK(cudaGetLastError());
+    return mi3d_packbits(density_grid, C * (n / 8), density_thresh, mean_density_out, bitfield, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+"""torch.autograd.Function wrappers over the fused field / render kernels of libmi3d.so.
+
+* ``field_eval``      -- NeRFNetwork.forward / density / normal on an explicit point set (B2 unfused seam)
+* ``render_train``    -- the whole training branch of NeRFRenderer.run_cuda (nerf/renderer.py:481-524,553-583):
+                         march (fused near/far, look-back compaction) -> fused field -> composite (+epilogue),
+                         three launches, zero host synchronisation; backward = composite-bwd + fused field-bwd.
+Gradients flow to (table, w1, b1, w2, b2, w3, b3) only, exactly the leaves the reference optimises
+(nerf/network_tcnn.py:195-206); positions get none (tcnn is asked for none).
+"""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib as L
+
+
+def make_hashgrid(n_levels=16, base_resolution=16, per_level_scale=1.3819128274917603, log2_hashmap_size=19):
+    hg = L.HashGrid()
+    L.check(L.lib().mi3d_hashgrid_make(C.c_uint32(n_levels), C.c_uint32(base_resolution), C.c_double(per_level_scale),
+                                       C.c_uint32(log2_hashmap_size), C.byref(hg)), "hashgrid_make")
+    return hg
+
+
+def _mlp_struct(ws):
+    m = L.Mlp()
+    for name, t in zip(("w1", "b1", "w2", "b2", "w3", "b3"), ws):
+        setattr(m, name, t.data_ptr())
+    return m
+
+
+def _cfg_struct(cfg, light_d):
+    c = L.FieldCfg()
+    c.bound = cfg["bound"]; c.blob_density = cfg["blob_density"]; c.blob_radius = cfg["blob_radius"]
+    c.n_evals = cfg["n_evals"]; c.shading = L.SHADING[cfg["shading"]]; c.ambient_ratio = cfg["ambient_ratio"]
+    c.light_d = light_d.data_ptr() if light_d is not None else None
+    return c
+
+
+def _check_params(table, ws):
+    L.require_cuda(table, *ws)
+    shapes = [(64, 32), (64,), (64, 64), (64,), (4, 64), (4,)]
+    for t, s in zip(ws, shapes):
+        if tuple(t.shape) != s or t.dtype != torch.float32 or not t.is_contiguous():
+            raise L.Mi3dError(f"sigma_net must be MLP(32,4,64,3) fp32 contiguous; got {tuple(t.shape)} {t.dtype}")
+    if table.dtype != torch.float32 or not table.is_contiguous():
+        raise L.Mi3dError("encoder.params must be a contiguous fp32 tensor")
+
+
+def _grad_or_none(g):
+    return None if g is None else L.f32c(g)
+
+
+class _FieldEval(Function):
+    """sigma, color, normal, loss_orient, loss_smooth = field(table, mlp..., xyzs, dirs, light_d)"""
+
+    @staticmethod
+    def forward(ctx, table, w1, b1, w2, b2, w3, b3, xyzs, dirs, light_d, smooth_noise, hg, cfg, seed):
+        ws = (w1, b1, w2, b2, w3, b3)
+        _check_params(table, ws)
+        xyzs = L.f32c(xyzs)
+        dirs = L.f32c(dirs) if dirs is not None else None
+        L.require_cuda(xyzs, dirs, light_d, smooth_noise)
+        m = xyzs.shape[0]
+        dev = xyzs.device
+        sigmas = torch.empty(m, dtype=torch.float32, device=dev)
+        rgbs = torch.empty(m, 3, dtype=torch.float32, device=dev)
+        normals = torch.empty(m, 3, dtype=torch.float32, device=dev) if cfg["n_evals"] >= 7 else None
+        tape = torch.empty(m, 16, dtype=torch.float32, device=dev)
+        nct = L.lib().mi3d_field_grid_ctas(C.c_int(0))
+        partials = torch.empty(2 * nct, dtype=torch.float32, device=dev)
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+        io = L.FieldIO()
+        io.xyzs = xyzs.data_ptr(); io.dirs = dirs.data_ptr() if dirs is not None else None
+        io.counter = None; io.m_fixed = m; io.align = 0; io.cap = m
+        io.smooth_noise = smooth_noise.data_ptr() if smooth_noise is not None else None
+        io.seed = seed
+        mlp, cf = _mlp_struct(ws), _cfg_struct(cfg, light_d)
+        if m > 0:
+            L.check(L.lib().mi3d_field_forward(C.byref(io), L.ptr(table), C.byref(hg), C.byref(mlp), C.byref(cf), L.ptr(sigmas),
+                                               L.ptr(rgbs), L.ptr(normals), L.ptr(tape), L.ptr(partials),
+                                               C.c_void_p(losses.data_ptr()), C.c_void_p(losses.data_ptr() + 4), L.stream()),
+                    "field_forward")
+        ctx.save_for_backward(table, w1, b1, w2, b2, w3, b3, xyzs, dirs, light_d, smooth_noise, tape)
+        ctx.hg, ctx.cfg, ctx.seed, ctx.m = hg, cfg, seed, m
+        if normals is None:
+            normals = torch.zeros(m, 3, dtype=torch.float32, device=dev)
+        return sigmas, rgbs, normals, losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_sigmas, g_rgbs, g_normals, g_lo, g_ls):
+        table, w1, b1, w2, b2, w3, b3, xyzs, dirs, light_d, smooth_noise, tape = ctx.saved_tensors
+        ws = (w1, b1, w2, b2, w3, b3)
+        g_table = torch.zeros_like(table)
+        g_ws = [torch.zeros_like(w) for w in ws]
+        if ctx.m > 0:
+            io = L.FieldIO()
+            io.xyzs = xyzs.data_ptr(); io.dirs = dirs.data_ptr() if dirs is not None else None
+            io.counter = None; io.m_fixed = ctx.m; io.align = 0; io.cap = ctx.m
+            io.smooth_noise = smooth_noise.data_ptr() if smooth_noise is not None else None
+            io.seed = ctx.seed
+            mlp, cf = _mlp_struct(ws), _cfg_struct(ctx.cfg, light_d)
+            gm = _mlp_struct(g_ws)
+            g_sigmas, g_rgbs, g_normals = _grad_or_none(g_sigmas), _grad_or_none(g_rgbs), _grad_or_none(g_normals)
+            g_lo, g_ls = _grad_or_none(g_lo), _grad_or_none(g_ls)
+            if ctx.cfg["n_evals"] < 7:
+                g_normals = None
+            L.check(L.lib().mi3d_field_backward(C.byref(io), L.ptr(table), C.byref(ctx.hg), C.byref(mlp), C.byref(cf), L.ptr(tape),
+                                                L.ptr(g_sigmas), L.ptr(g_rgbs), L.ptr(g_normals), L.ptr(g_lo), L.ptr(g_ls),
+                                                L.ptr(g_table), C.byref(gm), L.stream()), "field_backward")
+        return (g_table, *g_ws, None, None, None, None, None, None, None)
+
+
+def field_eval(table, mlp_params, xyzs, dirs, light_d, hg, cfg, smooth_noise=None, seed=0):
+    return _FieldEval.apply(table, *mlp_params, xyzs, dirs, light_d, smooth_noise, hg, cfg, seed)
+
+
+class RenderWorkspace:
+    """Capacity-sized per-sample buffers, allocated once and reused every step (no zero-fill, no empty_cache):
+    the 268 MB/step torch.zeros + allocator flush of raymarching.py:217-243 disappears."""
+
+    def __init__(self, N, max_steps, device, max_samples=None):
+        cap = N * max_steps if max_samples is None else min(N * max_steps, max_samples)
+        cap += 128  # room for the aligned zero rows the loss means include (raymarching.py:237-241)
+        self.N, self.cap, self.device = N, cap, device
+        f32 = dict(dtype=torch.float32, device=device)
+        self.xyzs = torch.empty(cap, 3, **f32)
+        self.dirs = torch.empty(cap, 3, **f32)
+        self.deltas = torch.empty(cap, 2, **f32)
+        self.sigmas = torch.empty(cap, **f32)
+        self.rgbs = torch.empty(cap, 3, **f32)
+        self.tape = torch.empty(cap, 16, **f32)
+        self.g_sigmas = torch.empty(cap, **f32)
+        self.g_rgbs = torch.empty(cap, 3, **f32)
+        self.rays = torch.empty(N, 3, dtype=torch.int32, device=device)
+        self.counter = torch.zeros(2, dtype=torch.int32, device=device)
+        self.nears = torch.empty(N, **f32)
+        self.fars = torch.empty(N, **f32)
+        self.ws_raw = torch.empty(N, **f32)
+        self.depth_raw = torch.empty(N, **f32)
+        self.image_raw = torch.empty(N, 3, **f32)
+        lib = L.lib()
+        self.scan_ws = torch.empty(lib.mi3d_march_rays_train_workspace_bytes(C.c_uint32(N)), dtype=torch.uint8, device=device)
+        self.partials = torch.empty(2 * lib.mi3d_field_grid_ctas(C.c_int(0)), **f32)
+        self.generation = 0
+
+
+class _RenderTrain(Function):
+    @staticmethod
+    def forward(ctx, table, w1, b1, w2, b2, w3, b3, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color,
+                depth_scale, ws, hg, cfg, opts):
+        P = (w1, b1, w2, b2, w3, b3)
+        _check_params(table, P)
+        rays_o, rays_d = L.f32c(rays_o).view(-1, 3), L.f32c(rays_d).view(-1, 3)
+        L.require_cuda(rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color, depth_scale)
+        N = rays_o.shape[0]
+        if N != ws.N:
+            raise L.Mi3dError(f"workspace built for {ws.N} rays, got {N}")
+        dev = rays_o.device
+        lib = L.lib()
+        ws.generation += 1
+        ws.counter.zero_()                                                     # renderer.py:504
+        L.check(lib.mi3d_march_rays_train(
+            L.ptr(rays_o), L.ptr(rays_d), L.ptr(bitfield), C.c_float(opts["bound"]), C.c_float(opts["dt_gamma"]),
+            C.c_uint32(opts["max_steps"]), C.c_uint32(N), C.c_uint32(opts["cascade"]), C.c_uint32(opts["grid_size"]),
+            C.c_uint32(ws.cap - 128), C.c_void_p(0), C.c_void_p(0), L.ptr(aabb), C.c_float(opts["min_near"]), L.ptr(ws.nears),
+            L.ptr(ws.fars), L.ptr(noises), C.c_uint64(opts["seed"]), L.ptr(ws.xyzs), L.ptr(ws.dirs), L.ptr(ws.deltas), L.ptr(ws.rays),
+            L.ptr(ws.counter), L.ptr(ws.scan_ws), L.stream()), "march_rays_train")
+        io = L.FieldIO()
+        io.xyzs = ws.xyzs.data_ptr(); io.dirs = ws.dirs.data_ptr(); io.counter = ws.counter.data_ptr()
+        io.m_fixed = 0; io.align = 128; io.cap = ws.cap
+        io.smooth_noise = smooth_noise.data_ptr() if smooth_noise is not None else None
+        io.seed = opts["seed"] + 1
+        mlp, cf = _mlp_struct(P), _cfg_struct(cfg, light_d)
+        losses = torch.zeros(2, dtype=torch.float32, device=dev)
+        L.check(lib.mi3d_field_forward(C.byref(io), L.ptr(table), C.byref(hg), C.byref(mlp), C.byref(cf), L.ptr(ws.sigmas),
+                                       L.ptr(ws.rgbs), C.c_void_p(0), L.ptr(ws.tape), L.ptr(ws.partials),
+                                       C.c_void_p(losses.data_ptr()), C.c_void_p(losses.data_ptr() + 4), L.stream()), "field_forward")
+        ep = L.Epilogue()
+        ep.bg_color = bg_color.data_ptr() if bg_color is not None else None
+        ep.bg_scalar = 1.0
+        ep.max_depth = opts["max_depth"]
+        ep.depth_scale = depth_scale.data_ptr() if depth_scale is not None else None
+        image = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        L.check(lib.mi3d_composite_rays_train_forward(
+            L.ptr(ws.sigmas), L.ptr(ws.rgbs), L.ptr(ws.deltas), L.ptr(ws.rays), C.c_uint32(ws.cap), C.c_uint32(N),
+            C.c_float(opts["T_thresh"]), L.ptr(ws.ws_raw), L.ptr(ws.depth_raw), L.ptr(ws.image_raw), C.byref(ep), L.ptr(image),
+            L.ptr(depth), L.stream()), "composite_rays_train_forward")
+        weights_sum = ws.ws_raw.clone()
+        ctx.save_for_backward(table, w1, b1, w2, b2, w3, b3, light_d, smooth_noise, bg_color, depth_scale)
+        ctx.ws, ctx.hg, ctx.cfg, ctx.opts, ctx.N, ctx.generation = ws, hg, cfg, opts, N, ws.generation
+        ctx.io_seed = io.seed
+        return image, depth, weights_sum, losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_image, g_depth, g_ws, g_lo, g_ls):
+        table, w1, b1, w2, b2, w3, b3, light_d, smooth_noise, bg_color, depth_scale = ctx.saved_tensors
+        ws, N, opts = ctx.ws, ctx.N, ctx.opts
+        if ws.generation != ctx.generation:
+            raise L.Mi3dError("render workspace was reused by a later forward before this backward ran")
+        P = (w1, b1, w2, b2, w3, b3)
+        lib = L.lib()
+        dev = table.device
+        g_image = L.f32c(g_image) if g_image is not None else torch.zeros(N, 3, dtype=torch.float32, device=dev)
+        g_depth, g_ws = _grad_or_none(g_depth), _grad_or_none(g_ws)
+        ep = L.Epilogue()
+        ep.bg_color = bg_color.data_ptr() if bg_color is not None else None
+        ep.bg_scalar = 1.0
+        ep.max_depth = opts["max_depth"]
+        ep.depth_scale = depth_scale.data_ptr() if depth_scale is not None else None
+        L.check(lib.mi3d_composite_rays_train_backward(
+            L.ptr(g_ws), L.ptr(g_image), L.ptr(g_depth), L.ptr(ws.sigmas), L.ptr(ws.rgbs), L.ptr(ws.deltas), L.ptr(ws.rays),
+            L.ptr(ws.ws_raw), L.ptr(ws.image_raw), C.c_uint32(ws.cap), C.c_uint32(N), C.c_float(opts["T_thresh"]), C.byref(ep),
+            L.ptr(ws.g_sigmas), L.ptr(ws.g_rgbs), C.c_int(1), L.stream()), "composite_rays_train_backward")
+        g_table = torch.zeros_like(table)
+        g_P = [torch.zeros_like(w) for w in P]
+        io = L.FieldIO()
+        io.xyzs = ws.xyzs.data_ptr(); io.dirs = ws.dirs.data_ptr(); io.counter = ws.counter.data_ptr()
+        io.m_fixed = 0; io.align = 128; io.cap = ws.cap
+        io.smooth_noise = smooth_noise.data_ptr() if smooth_noise is not None else None
+        io.seed = ctx.io_seed
+        mlp, cf, gm = _mlp_struct(P), _cfg_struct(ctx.cfg, light_d), _mlp_struct(g_P)
+        g_lo, g_ls = _grad_or_none(g_lo), _grad_or_none(g_ls)
+        L.check(lib.mi3d_field_backward(C.byref(io), L.ptr(table), C.byref(ctx.hg), C.byref(mlp), C.byref(cf), L.ptr(ws.tape),
+                                        L.ptr(ws.g_sigmas), L.ptr(ws.g_rgbs), C.c_void_p(0), L.ptr(g_lo), L.ptr(g_ls), L.ptr(g_table),
+                                        C.byref(gm), L.stream()), "field_backward")
+        return (g_table, *g_P) + (None,) * 13
+
+
+def render_train(table, mlp_params, rays_o, rays_d, bitfield, aabb, ws, hg, cfg, opts, noises=None, light_d=None,
+                 smooth_noise=None, bg_color=None, depth_scale=None):
+    """Returns (image[N,3], depth[N], weights_sum[N], loss_orient, loss_smooth)."""
+    return _RenderTrain.apply(table, *mlp_params, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color,
+                              depth_scale, ws, hg, cfg, opts)

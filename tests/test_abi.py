@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library builds for sm_100a, loads without a GPU, and exports exactly what include/mi3d.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "mi3d.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mi3d_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(mi3d):
+    lib = mi3d.lib()
+    syms = header_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(lib, s), f"libmi3d.so does not export {s}"
+    assert sorted(mi3d._lib.SYMBOLS) == syms
+    assert b"sm_100a" in lib.mi3d_version()
+
+
+def test_workspace_queries_are_pure_host(mi3d):
+    lib = mi3d.lib()
+    assert lib.mi3d_march_rays_train_workspace_bytes(ctypes.c_uint32(16384)) == (1 + 2 * 128) * 4
+    assert lib.mi3d_density_grid_workspace_bytes(ctypes.c_uint32(1), ctypes.c_uint32(128)) > 128 ** 3 * 16
+
+
+def test_hashgrid_geometry_matches_oracle(mi3d):
+    """Host helper mi3d_hashgrid_make vs the oracle's level table (tiny-cuda-nn grid.h geometry; SURVEY 8a-E1 sizes)."""
+    import importlib
+    from oracle import raymarch as orm
+    ops = importlib.import_module("make-it-3d_b200.nerf.field_ops")
+    hg = ops.make_hashgrid()
+    lv = orm.hashgrid_levels()
+    assert hg.n_levels == 16 and hg.n_entries == lv["total"] == 6098120
+    assert list(hg.sizes) == list(lv["sizes"]) and list(hg.offsets) == list(lv["offsets"]) and list(hg.ress) == list(lv["ress"])
+    assert list(hg.sizes)[:5] == [4096, 12168, 29792, 79512, 205384] and all(s == 524288 for s in list(hg.sizes)[5:])
+    assert all(abs(a - b) == 0 for a, b in zip(hg.scales, lv["scales"]))
+
+
+def test_product_path_refuses_cpu_tensors(mi3d):
+    """No CPU fallback: the operators raise on CPU tensors instead of silently computing elsewhere."""
+    import importlib
+    import pytest
+    import torch
+    ops = importlib.import_module("make-it-3d_b200.nerf.field_ops")
+    nt = importlib.import_module("make-it-3d_b200.nerf.network_tcnn")
+    enc = nt.HashGridEncoding()
+    with pytest.raises(mi3d.Mi3dError):
+        enc(torch.rand(4, 3))
+    assert ops is not None
+
+
+def test_state_dict_keys_match_reference(mi3d):
+    """nerf/utils.py:1075-1186 checkpoints: same keys / shapes as the reference module tree."""
+    import argparse
+    import importlib
+    nt = importlib.import_module("make-it-3d_b200.nerf.network_tcnn")
+    opt = argparse.Namespace(bound=1, min_near=0.1, density_thresh=10, bg_radius=-1, blob_density=5, blob_radius=0.1,
+                             lambda_smooth=1, max_depth=10.0)
+    sd = nt.NeRFNetwork(opt).state_dict()
+    want = {'aabb_train': (6,), 'aabb_infer': (6,), 'density_grid': (1, 128 ** 3), 'density_bitfield': (128 ** 3 // 8,),
+            'step_counter': (16, 2), 'encoder.params': (12196240,), 'sigma_net.net.0.weight': (64, 32), 'sigma_net.net.0.bias': (64,),
+            'sigma_net.net.1.weight': (64, 64), 'sigma_net.net.1.bias': (64,), 'sigma_net.net.2.weight': (4, 64),
+            'sigma_net.net.2.bias': (4,)}
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want

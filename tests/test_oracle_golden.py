@@ -1,0 +1,128 @@
+"""CPU: pin the oracle (oracle/) against the golden vectors produced by the reference's own Python
+(tests/golden/make_golden.py) and check the C and torch restatements against each other."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import field_from_golden, fr, make_table, max_abs, orm, rel_err, sphere_bitfield
+
+
+def test_small_ops_match_reference_vectors():
+    g = load_golden("small_ops.npz")
+    x = torch.from_numpy(g["te_x"]).requires_grad_()
+    y = fr._TruncExp.apply(x)
+    y.sum().backward()
+    np.testing.assert_array_equal(y.detach().numpy(), g["te_y"])          # activation.py:5-16
+    np.testing.assert_array_equal(x.grad.numpy(), g["te_g"])
+    ro, rd, sc = fr.get_rays_ref(g["pose"], (40.0, 42.0, 8.0, 7.5), 15, 16)   # nerf/utils.py:51-116
+    np.testing.assert_allclose(ro.numpy(), g["rays_o"], rtol=0, atol=0)
+    np.testing.assert_allclose(rd.numpy(), g["rays_d"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(sc.numpy(), g["depth_scale"], rtol=1e-6)
+    np.testing.assert_array_equal(fr.safe_normalize(torch.from_numpy(g["sn_in"])).numpy(), g["sn_out"])
+
+
+def test_morton_packbits_roundtrip():
+    rng = np.random.default_rng(0)
+    coords = rng.integers(0, 1024, size=(5000, 3), dtype=np.int32)
+    idx = orm.morton3D(coords)
+    np.testing.assert_array_equal(orm.morton3D_invert(idx), coords)
+    # bit layout known-answer: x -> bit 0, y -> bit 1, z -> bit 2 (raymarching.cu:65-71)
+    np.testing.assert_array_equal(orm.morton3D(np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [3, 0, 0], [127, 127, 127]], np.int32)),
+                                  [1, 2, 4, 9, 2 ** 21 - 1])
+    grid = rng.random(1024, dtype=np.float32)
+    bits = orm.packbits(grid, 0.5)
+    np.testing.assert_array_equal(np.unpackbits(bits, bitorder="little").astype(bool), grid > 0.5)
+
+
+def test_hashgrid_c_vs_torch_restatement():
+    """Two independent restatements of tiny-cuda-nn's HashGrid (C loops vs vectorised torch) agree, incl. x = 0 and x = 1."""
+    lv = orm.hashgrid_levels()
+    table = make_table(lv["total"] * 2, 5, 1.0)
+    rng = np.random.default_rng(1)
+    x = rng.random((4000, 3), dtype=np.float32)
+    x[:8] = np.array([[0, 0, 0], [1, 1, 1], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0.5, 0.5, 0.5], [1, 1, 0], [0.999999, 1e-7, 0.25]], np.float32)
+    out_c = orm.hashgrid_forward(x, table, lv)
+    enc = fr.HashGridRef()
+    with torch.no_grad():
+        enc.params.copy_(torch.from_numpy(table))
+        out_t = enc(torch.from_numpy(x)).numpy()
+    assert max_abs(out_c, out_t) < 2e-6
+
+
+def test_march_properties_and_determinism():
+    from helpers import camera_rays
+    ro, rd, _ = camera_rays(32)
+    bits = sphere_bitfield(0.3)
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    nears, fars = orm.near_far_from_aabb(ro, rd, aabb, 0.2)
+    noises = np.random.default_rng(2).random(ro.shape[0], dtype=np.float32)
+    x1, d1, dl1, r1, tot1 = orm.march_rays_train(ro, rd, 1.0, bits, 1, 128, nears, fars, noises, 0.0, 512, align=128)
+    x2, d2, dl2, r2, tot2 = orm.march_rays_train(ro, rd, 1.0, bits, 1, 128, nears, fars, noises, 0.0, 512, align=128)
+    assert tot1 == tot2 and np.array_equal(x1, x2) and np.array_equal(r1, r2)
+    assert x1.shape[0] % 128 == 0 and x1.shape[0] > tot1                       # raymarching.py:237-241 padding rule
+    assert np.all(r1[:, 0] == np.arange(ro.shape[0])) and np.all(np.diff(r1[:, 1]) == r1[:-1, 2])   # ray-id ordered compaction
+    assert np.all(np.linalg.norm(x1[:tot1], axis=1) < 0.3 + 2.0 / 128 * np.sqrt(3)) and tot1 > 1000  # samples lie in occupied cells
+    dt_min = np.float32(2 * np.sqrt(3) / 512)
+    assert np.all(dl1[:tot1, 0] == dt_min) and np.all(dl1[:tot1, 1] >= dt_min * 0.999)
+    assert np.all(x1[tot1:] == 0)
+    # empty grid -> no samples, composite gives zeros
+    x0, _, _, r0, tot0 = orm.march_rays_train(ro, rd, 1.0, np.zeros_like(bits), 1, 128, nears, fars, noises, 0.0, 512, align=128)
+    assert tot0 == 0 and np.all(r0[:, 2] == 0)
+    ws, dep, img = orm.composite_rays_train_forward(np.zeros(x0.shape[0], np.float32), np.zeros((x0.shape[0], 3), np.float32),
+                                                    np.zeros((x0.shape[0], 2), np.float32), r0)
+    assert not ws.any() and not dep.any() and not img.any()
+
+
+def test_composite_backward_matches_autograd_of_formula():
+    """raymarching.cu:602-682 analytic gradient == torch autograd of the plain compositing formula (no early-out)."""
+    rng = np.random.default_rng(3)
+    counts = np.array([5, 0, 17, 1, 9], np.int32)
+    offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int32)
+    rays = np.stack([np.arange(5, dtype=np.int32), offs, counts], 1)
+    M = int(counts.sum())
+    sig = (rng.random(M, dtype=np.float32) * 3).astype(np.float32)
+    rgb = rng.random((M, 3), dtype=np.float32)
+    dl = np.stack([np.full(M, 0.05, np.float32), np.full(M, 0.05, np.float32)], 1)
+    gw, gi = rng.standard_normal(5).astype(np.float32), rng.standard_normal((5, 3)).astype(np.float32)
+    ws, dep, img = orm.composite_rays_train_forward(sig, rgb, dl, rays, 0.0)
+    gs, gr = orm.composite_rays_train_backward(gw, gi, sig, rgb, dl, rays, ws, img, 0.0)
+    s_t, c_t = torch.from_numpy(sig).double().requires_grad_(), torch.from_numpy(rgb).double().requires_grad_()
+    loss = 0
+    for n in range(5):
+        o, c = offs[n], counts[n]
+        if c == 0:
+            continue
+        alpha = 1 - torch.exp(-s_t[o:o + c] * 0.05)
+        T = torch.cumprod(torch.cat([torch.ones(1, dtype=torch.double), 1 - alpha[:-1]]), 0)
+        w = alpha * T
+        loss = loss + (w.sum() * float(gw[n])) + ((w[:, None] * c_t[o:o + c]).sum(0) * torch.from_numpy(gi[n]).double()).sum()
+    loss.backward()
+    assert max_abs(gs, s_t.grad.numpy()) < 5e-6 and max_abs(gr, c_t.grad.numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["albedo"])
+def test_render_restatement_matches_reference_python(case):
+    """oracle.field_ref.render_train_ref (our restatement of run_cuda + NeRFNetwork) == the REFERENCE's own
+    nerf/renderer.py + nerf/network_tcnn.py output recorded in tests/golden (forward + gradients)."""
+    g = load_golden(f"render_{case}.npz")
+    field, _ = field_from_golden(g)
+    bits = sphere_bitfield(float(g["radius"]))
+    out = fr.render_train_ref(field, g["rays_o"], g["rays_d"], bits, noises=g["noises"], light_d=g["light_d"],
+                              smooth_noise=g["smooth_noise"], bg_color=g["bg_color"], depth_scale=g["depth_scale"], max_steps=512,
+                              ambient_ratio=float(g["ratio"]), shading=str(g["shading"]), lambda_smooth=1.0)
+    assert out["total"] == int(g["total"]) and out["xyzs"].shape[0] == int(g["m_pad"])
+    assert max_abs(out["image"].detach(), g["image"]) < 1e-6
+    assert max_abs(out["depth"].detach(), g["depth"]) < 1e-5
+    assert max_abs(out["weights_sum"].detach(), g["weights_sum"]) < 1e-6
+    assert abs(out["loss_orient"].item() - float(g["loss_orient"])) < 1e-6
+    assert abs(out["loss_smooth"].item() - float(g["loss_smooth"])) < 1e-6
+    loss = (out["image"] * torch.from_numpy(g["A"])).sum() + (out["weights_sum"] * torch.from_numpy(g["B"])).sum() \
+        + (out["depth"] * torch.from_numpy(g["Cd"])).sum() + 30.0 * out["loss_orient"] + 50.0 * out["loss_smooth"]
+    loss.backward()
+    for l, (w, b) in enumerate((("g_w1", "g_b1"), ("g_w2", "g_b2"), ("g_w3", "g_b3"))):
+        assert rel_err(field.sigma_net.net[l].weight.grad.numpy(), g[w], floor=1e-3) < 1e-3
+        assert rel_err(field.sigma_net.net[l].bias.grad.numpy(), g[b], floor=1e-3) < 1e-3
+    gt = field.encoder.params.grad.numpy()
+    assert rel_err(gt[g["g_table_idx"]], g["g_table_val"], floor=1e-4) < 1e-3
+    assert abs(np.sqrt((gt.astype(np.float64) ** 2).sum()) / float(g["g_table_l2"]) - 1) < 1e-5
