@@ -173,6 +173,23 @@ int mi3d_density_grid_update(float* density_grid, uint8_t* density_bitfield, uin
                              const mi3d_mlp* mlp, const mi3d_field_cfg* cfg, const float* jitter, uint64_t seed,
                              float* mean_density_out, void* workspace, mi3d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * B3: Stable-Diffusion guidance  (replaces the diffusers/cuDNN/cuBLAS calls behind nerf/sd.py:117-174, :212-220)
+ * ------------------------------------------------------------------------------------------------------ */
+
+/* The one tensor-core tile kernel (tcgen05.mma + TMEM accumulators + TMA operand staging) exposed directly:
+ *   out[M,N] = alpha * A[M,K] . B[N,K]^T + bias[N] (+ residual[M,N]);  A, B fp16 K-major; out fp16 or fp32.
+ * Stands in for the cuBLAS GEMM under every nn.Linear of diffusers' UNet2DConditionModel / AutoencoderKL
+ * (nerf/sd.py:146, :217).  M % 128 == 0, K % 64 == 0, N % block_n == 0 (block_n in {64,128,256}; 0 = auto).
+ * epi_mode: 0 plain, 1 GEGLU (rows of B interleaved value/gate; out is [M, N/2]), 2 transposed store (out is [N, M]). */
+int mi3d_gemm_f16(const void* a, const void* b, void* out, int out_is_f32, int M, int N, int K, int block_n, float alpha,
+                  const float* bias, const void* residual, int epi_mode, mi3d_stream_t stream);
+
+/* Implicit-GEMM 3x3 stride-1 pad-1 convolution on the same kernel (stands in for the cuDNN conv under diffusers'
+ * ResnetBlock2D / Downsample2D / Upsample2D): x [N,H,W,Cin] fp16 NHWC, w [Cout][3][3][Cin] fp16, y [N,H,W,Cout] fp16. */
+int mi3d_conv3x3_f16(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, int block_n,
+                     const float* bias, const void* residual, mi3d_stream_t stream);
+
 const char* mi3d_version(void);
 
 #ifdef __cplusplus

@@ -51,6 +51,7 @@ SYMBOLS = [
     "mi3d_hashgrid_make", "mi3d_hashgrid_forward", "mi3d_hashgrid_backward",
     "mi3d_field_grid_ctas", "mi3d_field_forward", "mi3d_field_backward",
     "mi3d_density_grid_workspace_bytes", "mi3d_density_grid_update", "mi3d_version",
+    "mi3d_gemm_f16", "mi3d_conv3x3_f16",
 ]
 
 

@@ -77,7 +77,8 @@ def test_field_forward_backward_vs_torch_oracle(shading, ratio):
     sig, col, nrm = net(_cu(x), _cu(d), _cu(l), ratio=ratio, shading=shading)
     sig_r, col_r, nrm_r = field(torch.from_numpy(x), torch.from_numpy(d), torch.from_numpy(l), ratio=ratio, shading=shading)
     assert rel_err(sig.detach().cpu(), sig_r.detach(), floor=1e-3) < 2e-5
-    assert max_abs(col.detach().cpu(), col_r.detach()) < 2e-5
+    # lit colours inherit the normal's fp32 cancellation error (<= 5e-4 on a unit vector)
+    assert max_abs(col.detach().cpu(), col_r.detach()) < (2e-5 if shading == 'albedo' else 5e-4)
     # normals difference two densities 0.02 apart: allow 5e-4 absolute on unit vectors (fp32 cancellation)
     assert max_abs(nrm.detach().cpu(), nrm_r.detach()) < 5e-4
     gs, gc, gn = rng.standard_normal(m).astype(np.float32), rng.standard_normal((m, 3)).astype(np.float32), rng.standard_normal((m, 3)).astype(np.float32) * 0.1

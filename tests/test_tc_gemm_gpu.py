@@ -1,0 +1,77 @@
+"""GPU: the tcgen05/TMEM/TMA tile kernel vs a plain PyTorch fp32 reference of the same op (floating-point kernel:
+torch fp32 is the stated checker).  Inputs are fp16; products are exact in fp32, accumulation order differs -> the
+bound is K * eps_fp32 * |a||b| plus one fp16 rounding of the output (2^-11 relative)."""
+import ctypes as C
+import importlib
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    return importlib.import_module("make-it-3d_b200._lib")
+
+
+def _gemm(L, a, b, out_f32=False, block_n=0, alpha=1.0, bias=None, residual=None, epi=0):
+    M, K = a.shape
+    N = b.shape[0]
+    shape = (M, N // 2) if epi == 1 else ((N, M) if epi == 2 else (M, N))
+    out = torch.empty(shape, dtype=torch.float32 if out_f32 else torch.float16, device="cuda")
+    L.check(L.lib().mi3d_gemm_f16(L.ptr(a), L.ptr(b), L.ptr(out), C.c_int(int(out_f32)), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(block_n),
+                                  C.c_float(alpha), L.ptr(bias), L.ptr(residual), C.c_int(epi), L.stream()), "gemm_f16")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (128, 128, 128, 128), (256, 256, 512, 256), (1024, 320, 320, 64),
+                                      (8192, 640, 1280, 128), (512, 1280, 11520, 256), (128, 2560, 64, 0), (384, 192, 4096, 64)])
+def test_gemm_matches_fp32_reference(L, M, N, K, bn):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g)).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    ref = a.float() @ b.float().t()
+    out = _gemm(L, a, b, out_f32=True, block_n=bn)
+    err = (out - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), err     # fp32 accumulate: observed ~1e-5
+    out16 = _gemm(L, a, b, block_n=bn)
+    assert (out16.float() - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_epilogues(L):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 256, 256, 192
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).half()
+    ref = 0.5 * (a.float() @ b.float().t()) + bias + res.float()
+    out = _gemm(L, a, b, out_f32=True, alpha=0.5, bias=bias, residual=res, block_n=128)
+    assert (out - ref).abs().max().item() < 1e-3
+    # GEGLU: B rows interleaved (value, gate) -> out[:, j] = value_j * gelu(gate_j)
+    full = a.float() @ b.float().t() + bias
+    val, gate = full[:, 0::2], full[:, 1::2]
+    ref_g = val * torch.nn.functional.gelu(gate)
+    out_g = _gemm(L, a, b, bias=bias, epi=1, block_n=64)
+    assert (out_g.float() - ref_g).abs().max().item() < 4e-3
+    # transposed store
+    out_t = _gemm(L, a, b, epi=2, block_n=64)
+    assert (out_t.float() - (a.float() @ b.float().t()).t()).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin,Cout", [(2, 8, 8, 64, 64), (2, 16, 16, 128, 128), (2, 64, 64, 320, 320), (1, 128, 128, 128, 256),
+                                               (2, 32, 32, 640, 1280), (1, 256, 256, 64, 64)])
+def test_implicit_conv3x3_matches_fp32_reference(L, Nimg, H, W, Cin, Cout):
+    g = torch.Generator(device="cuda").manual_seed(H + Cin)
+    x = torch.randn(Nimg, H, W, Cin, device="cuda", generator=g).half()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) / (9 * Cin) ** 0.5).half()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    y = torch.empty(Nimg, H, W, Cout, dtype=torch.float16, device="cuda")
+    L.check(L.lib().mi3d_conv3x3_f16(L.ptr(x), L.ptr(w), L.ptr(y), C.c_int(Nimg), C.c_int(H), C.c_int(W), C.c_int(Cin), C.c_int(Cout),
+                                     C.c_int(0), L.ptr(bias), C.c_void_p(0), L.stream()), "conv3x3_f16")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    err = (y.float() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
