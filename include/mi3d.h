@@ -190,6 +190,61 @@ int mi3d_gemm_f16(const void* a, const void* b, void* out, int out_is_f32, int M
 int mi3d_conv3x3_f16(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, int block_n,
                      const float* bias, const void* residual, mi3d_stream_t stream);
 
+/* Stable-Diffusion engine: a statically planned launch list over the tile kernel above + memory-bound kernels.
+ * Configuration mirrors diffusers' UNet2DConditionModel / AutoencoderKL config.json fields that nerf/sd.py:41,53 load. */
+typedef struct {
+    int in_ch, out_ch;        /* 4, 4 */
+    int n_levels;             /* len(block_out_channels): 4 for SD-2.0-base; 0 = no U-Net in this engine */
+    int block_out[4];         /* 320, 640, 1280, 1280 */
+    int layers_per_block;     /* 2 */
+    int heads[4];             /* 5, 10, 20, 20 (head_dim 64) */
+    int cross_dim;            /* 1024 */
+    int ctx_len;              /* 77 text tokens */
+    int groups;               /* 32 */
+    int latent_hw;            /* 64 (nerf/sd.py:124 always feeds 512x512 -> 64x64 latents) */
+    int batch;                /* 2 = [uncond, text] (nerf/sd.py:143) */
+} mi3d_unet_cfg;
+
+typedef struct {
+    int in_ch, latent_ch;     /* 3, 4 */
+    int n_levels;             /* 4; 0 = no VAE in this engine */
+    int block_out[4];         /* 128, 256, 512, 512 */
+    int layers_per_block;     /* 2 */
+    int groups;               /* 32 */
+    int image_hw;             /* 512 */
+} mi3d_vae_cfg;
+
+typedef struct mi3d_sd* mi3d_sd_t;
+
+/* HOST: bytes of device workspace the engine needs (weights + activations + tapes; nothing else is ever allocated) */
+size_t mi3d_sd_workspace_bytes(const mi3d_unet_cfg* unet, const mi3d_vae_cfg* vae);
+/* HOST: plans the launch lists inside `workspace` (device memory owned by the caller); NULL on failure */
+mi3d_sd_t mi3d_sd_create(const mi3d_unet_cfg* unet, const mi3d_vae_cfg* vae, void* workspace, size_t workspace_bytes);
+void mi3d_sd_destroy(mi3d_sd_t h);
+
+/* Parameters are enumerated by their diffusers state_dict names ("down_blocks.0.resnets.0.conv1.weight", VAE names are
+ * prefixed as in AutoencoderKL: "encoder....", "quant_conv...."; a '#...' suffix marks a derived copy of the base tensor).
+ * load: src = fp32 DEVICE tensor in the diffusers layout; partner_src = the matching ".bias" for GEGLU proj weights. */
+int mi3d_sd_num_params(mi3d_sd_t h);
+const char* mi3d_sd_param_name(mi3d_sd_t h, int i);
+long long mi3d_sd_param_numel(mi3d_sd_t h, int i);
+int mi3d_sd_param_shape(mi3d_sd_t h, int i, int* shape4); /* returns rank */
+int mi3d_sd_load_param(mi3d_sd_t h, int i, const float* src, const float* partner_src, mi3d_stream_t stream);
+
+/* replaces nerf/sd.py:124 (F.interpolate to 512) + :133,212-220 (encode_imgs: vae.encode(2x-1).latent_dist.sample()*0.18215)
+ * pred_rgb [1,3,H,W] fp32 in [0,1]; eps_posterior, latents [1,4,h,w] fp32 (h = image_hw/8). */
+int mi3d_sd_encode(mi3d_sd_t h, const float* pred_rgb, int H, int W, const float* eps_posterior, float* latents, mi3d_stream_t stream);
+/* the autograd half of latents.backward(gradient=grad) (nerf/sd.py:171): d latents -> d pred_rgb, weights frozen */
+int mi3d_sd_encode_backward(mi3d_sd_t h, const float* grad_latents, const float* eps_posterior, int H, int W, float* grad_pred_rgb,
+                            mi3d_stream_t stream);
+/* replaces nerf/sd.py:138-170: scheduler.add_noise, unet([x,x], t, text_embeddings).sample, CFG (text + gs*(text-uncond)),
+ * w = 1 - alphas[t], grad = nan_to_num(w*(noise_pred - noise)).  t: DEVICE int64 scalar; alphas_cumprod: DEVICE fp32 [1000];
+ * text_embeddings fp32 [2,77,cross_dim] (uncond first); noise_pred / grad (nullable) fp32 [1,4,h,w]. */
+int mi3d_sd_unet_sds(mi3d_sd_t h, const float* latents, const float* noise, const long long* t, const float* alphas_cumprod,
+                     const float* text_embeddings, float guidance_scale, float* noise_pred, float* grad, mi3d_stream_t stream);
+/* debug tap: device pointer + size of a named intermediate ("unet.mid", "vae.grad_in", ...) */
+int mi3d_sd_debug_tensor(mi3d_sd_t h, const char* name, void** ptr, size_t* bytes);
+
 const char* mi3d_version(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,466 @@
+// sd_kernels.cuh -- the memory-bound kernels around the tensor-core tiles of the SD guidance path: normalisations,
+// softmax, small direct convolutions, layout movers, latent arithmetic.  All activations are NHWC fp16 ("tokens x C"),
+// statistics and reductions are fp32 (fp64 for the GroupNorm group sums).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sdk {
+
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad(float x) { const float s = 1.f / (1.f + __expf(-x)); return s * (1.f + x * (1.f - s)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// parameter conversion (run once at load time)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_f32_to_f16(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2half_rn(src[i]);
+}
+// conv weight OIHW fp32 -> [O][ky][kx][I] fp16 ; if flip: dgrad layout [I][2-ky][2-kx][O]
+__global__ void k_conv_w(const float* __restrict__ src, __half* __restrict__ dst, int O, int I, int flip) {
+    const size_t n = (size_t)O * I * 9;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int kx = i % 3, ky = (i / 3) % 3, ci = (i / 9) % I, co = i / (9 * (size_t)I);
+        const float v = src[i];
+        if (!flip) dst[(((size_t)co * 3 + ky) * 3 + kx) * I + ci] = __float2half_rn(v);
+        else dst[(((size_t)ci * 3 + (2 - ky)) * 3 + (2 - kx)) * O + co] = __float2half_rn(v);
+    }
+}
+// linear [O][I] fp32 -> transposed [I][O] fp16
+__global__ void k_transpose_w(const float* __restrict__ src, __half* __restrict__ dst, int O, int I) {
+    const size_t n = (size_t)O * I;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int ci = i % I, co = i / I;
+        dst[(size_t)ci * O + co] = __float2half_rn(src[i]);
+    }
+}
+// GEGLU proj [2*inner][I]: rows (value_j | gate_j) -> interleaved rows 2j, 2j+1 ; bias likewise (fp32)
+__global__ void k_geglu_w(const float* __restrict__ w, const float* __restrict__ b, __half* __restrict__ wd, float* __restrict__ bd, int inner, int I) {
+    const size_t n = (size_t)2 * inner * I;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int ci = i % I; const int r = i / I;
+        const int j = r < inner ? r : r - inner, dst_r = 2 * j + (r < inner ? 0 : 1);
+        wd[(size_t)dst_r * I + ci] = __float2half_rn(w[i]);
+        if (ci == 0) bd[dst_r] = b[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GroupNorm (+ SiLU) over NHWC fp16.  Pass 1: per-(n, group) sum / sum of squares in fp64 via block partials + atomics.
+// ------------------------------------------------------------------------------------------------------------
+// grid (chunks, N); each CTA covers `pix_per_cta` pixels of image n; thread handles 8 channels of a pixel per iteration.
+__global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, int pix_per_cta, double* __restrict__ stats /*[N][G][2]*/) {
+    extern __shared__ float sm[];                 // [G][2]
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int vec_per_pix = C / 8;
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    const size_t base = (size_t)n * HW * C;
+    // a vector of 8 channels spans at most two groups (cpg >= 4 here): accumulate both in registers per vector
+    for (long long i = (long long)p0 * vec_per_pix + threadIdx.x; i < (long long)p1 * vec_per_pix; i += blockDim.x) {
+        const int cv = (int)(i % vec_per_pix);
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + base + (size_t)i * 8);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+        const int g0 = (cv * 8) / cpg;
+        if (cpg >= 8) {
+            float s0 = 0.f, ss0 = 0.f, s1 = 0.f, ss1 = 0.f;
+            #pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float v = __half2float(h[k]);
+                if ((cv * 8 + k) / cpg == g0) { s0 += v; ss0 += v * v; } else { s1 += v; ss1 += v * v; }
+            }
+            atomicAdd(&sm[2 * g0], s0); atomicAdd(&sm[2 * g0 + 1], ss0);
+            if ((cv * 8 + 7) / cpg != g0) { atomicAdd(&sm[2 * g0 + 2], s1); atomicAdd(&sm[2 * g0 + 3], ss1); }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 8; k++) { const float v = __half2float(h[k]); const int gg = (cv * 8 + k) / cpg; atomicAdd(&sm[2 * gg], v); atomicAdd(&sm[2 * gg + 1], v * v); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(size_t)n * 2 * G + i], (double)sm[i]);
+}
+
+// y = act((x - mean) * rstd * gamma + beta); act = SiLU if silu != 0.  total = N*HW*C/8 vectors.
+__global__ void k_gn_apply(const __half* __restrict__ x, __half* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, int HW, int C, int G, float eps, int do_silu, size_t total_vec) {
+    const int cpg = C / G, vec_per_pix = C / 8;
+    const double cnt = (double)HW * cpg;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % vec_per_pix);
+        const int n = (int)(i / ((size_t)vec_per_pix * HW));
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + i * 8);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+        __align__(16) __half o[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = cv * 8 + k, g = c / cpg;
+            const double m = stats[((size_t)n * G + g) * 2] / cnt;
+            const double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
+            const float rstd = rsqrtf((float)var + eps);
+            float v = (__half2float(h[k]) - (float)m) * rstd * gamma[c] + beta[c];
+            if (do_silu) v = silu(v);
+            o[k] = __float2half_rn(v);
+        }
+        *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+// GroupNorm(+SiLU) backward, pass 1: per-(n,group) sums of dz*gamma and dz*gamma*xhat (dz = dy * silu'(z) when do_silu)
+__global__ void k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dy, const double* __restrict__ stats,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G, float eps, int do_silu,
+                               int pix_per_cta, double* __restrict__ bstats /*[N][G][2]*/) {
+    extern __shared__ float sm[];
+    const int n = blockIdx.y, cpg = C / G, vec_per_pix = C / 8;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const double cnt = (double)HW * cpg;
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    const size_t base = (size_t)n * HW * C;
+    for (long long i = (long long)p0 * vec_per_pix + threadIdx.x; i < (long long)p1 * vec_per_pix; i += blockDim.x) {
+        const int cv = (int)(i % vec_per_pix);
+        const uint4 rx = *reinterpret_cast<const uint4*>(x + base + (size_t)i * 8);
+        const uint4 rd = *reinterpret_cast<const uint4*>(dy + base + (size_t)i * 8);
+        const __half* hx = reinterpret_cast<const __half*>(&rx); const __half* hd = reinterpret_cast<const __half*>(&rd);
+        #pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = cv * 8 + k, g = c / cpg;
+            const double m = stats[((size_t)n * G + g) * 2] / cnt;
+            const double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
+            const float rstd = rsqrtf((float)var + eps);
+            const float xh = (__half2float(hx[k]) - (float)m) * rstd;
+            float d = __half2float(hd[k]);
+            if (do_silu) d *= silu_grad(xh * gamma[c] + beta[c]);
+            const float dg = d * gamma[c];
+            atomicAdd(&sm[2 * g], dg); atomicAdd(&sm[2 * g + 1], dg * xh);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&bstats[(size_t)n * 2 * G + i], (double)sm[i]);
+}
+// pass 2: dx = rstd * (dg - mean(dg) - xhat * mean(dg*xhat)) (+ add, optional accumulation of another gradient branch)
+__global__ void k_gn_bwd_apply(const __half* __restrict__ x, const __half* __restrict__ dy, const double* __restrict__ stats,
+                               const double* __restrict__ bstats, const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
+                               int G, float eps, int do_silu, const __half* __restrict__ add, __half* __restrict__ dx, size_t total_vec) {
+    const int cpg = C / G, vec_per_pix = C / 8;
+    const double cnt = (double)HW * cpg;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % vec_per_pix);
+        const int n = (int)(i / ((size_t)vec_per_pix * HW));
+        const uint4 rx = *reinterpret_cast<const uint4*>(x + i * 8);
+        const uint4 rd = *reinterpret_cast<const uint4*>(dy + i * 8);
+        uint4 ra = make_uint4(0, 0, 0, 0);
+        if (add) ra = *reinterpret_cast<const uint4*>(add + i * 8);
+        const __half* hx = reinterpret_cast<const __half*>(&rx); const __half* hd = reinterpret_cast<const __half*>(&rd);
+        const __half* ha = reinterpret_cast<const __half*>(&ra);
+        __align__(16) __half o[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = cv * 8 + k, g = c / cpg;
+            const double m = stats[((size_t)n * G + g) * 2] / cnt;
+            const double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
+            const float rstd = rsqrtf((float)var + eps);
+            const float xh = (__half2float(hx[k]) - (float)m) * rstd;
+            float d = __half2float(hd[k]);
+            if (do_silu) d *= silu_grad(xh * gamma[c] + beta[c]);
+            const float dg = d * gamma[c];
+            const float m1 = (float)(bstats[((size_t)n * G + g) * 2] / cnt), m2 = (float)(bstats[((size_t)n * G + g) * 2 + 1] / cnt);
+            float v = rstd * (dg - m1 - xh * m2);
+            if (add) v += __half2float(ha[k]);
+            o[k] = __float2half_rn(v);
+        }
+        *reinterpret_cast<uint4*>(dx + i * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (C), one warp per row
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_layernorm(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            int rows, int C, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __half* xr = x + (size_t)row * C;
+    float s = 0.f, ss = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(xr + c);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+        #pragma unroll
+        for (int k = 0; k < 8; k++) { const float v = __half2float(h[k]); s += v; ss += v * v; }
+    }
+    s = warp_sum(s); ss = warp_sum(ss);
+    const float mean = s / C, var = fmaxf(ss / C - mean * mean, 0.f), rstd = rsqrtf(var + eps);
+    __half* yr = y + (size_t)row * C;
+    for (int c = lane * 8; c < C; c += 256) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(xr + c);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+        __align__(16) __half o[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = __float2half_rn((__half2float(h[k]) - mean) * rstd * gamma[c + k] + beta[c + k]);
+        *reinterpret_cast<uint4*>(yr + c) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// row softmax in place: p = softmax(scale * s[:, :valid]); columns >= valid are written as 0.  One warp per row.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_softmax(__half* __restrict__ s, size_t rows, int cols, int valid, float scale) {
+    const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    __half* r = s + row * cols;
+    float mx = -INFINITY;
+    for (int c = lane * 8; c < cols; c += 256) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(r + c);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+        #pragma unroll
+        for (int k = 0; k < 8; k++) if (c + k < valid) mx = fmaxf(mx, __half2float(h[k]) * scale);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int c = lane * 8; c < cols; c += 256) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(r + c);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+        #pragma unroll
+        for (int k = 0; k < 8; k++) if (c + k < valid) sum += __expf(__half2float(h[k]) * scale - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int c = lane * 8; c < cols; c += 256) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(r + c);
+        const __half* h = reinterpret_cast<const __half*>(&raw);
+        __align__(16) __half o[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = __float2half_rn(c + k < valid ? __expf(__half2float(h[k]) * scale - mx) * inv : 0.f);
+        *reinterpret_cast<uint4*>(r + c) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+// softmax backward in place on dp: ds = scale * p * (dp - sum(dp * p))
+__global__ void k_softmax_bwd(const __half* __restrict__ p, __half* __restrict__ dp, size_t rows, int cols, float scale) {
+    const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __half* pr = p + row * cols; __half* dr = dp + row * cols;
+    float dot = 0.f;
+    for (int c = lane * 8; c < cols; c += 256) {
+        const uint4 a = *reinterpret_cast<const uint4*>(pr + c); const uint4 b = *reinterpret_cast<const uint4*>(dr + c);
+        const __half* ha = reinterpret_cast<const __half*>(&a); const __half* hb = reinterpret_cast<const __half*>(&b);
+        #pragma unroll
+        for (int k = 0; k < 8; k++) dot += __half2float(ha[k]) * __half2float(hb[k]);
+    }
+    dot = warp_sum(dot);
+    for (int c = lane * 8; c < cols; c += 256) {
+        const uint4 a = *reinterpret_cast<const uint4*>(pr + c); const uint4 b = *reinterpret_cast<const uint4*>(dr + c);
+        const __half* ha = reinterpret_cast<const __half*>(&a); const __half* hb = reinterpret_cast<const __half*>(&b);
+        __align__(16) __half o[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = __float2half_rn(scale * __half2float(ha[k]) * (__half2float(hb[k]) - dot));
+        *reinterpret_cast<uint4*>(dr + c) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// layout movers
+// ------------------------------------------------------------------------------------------------------------
+// batched 2-D transpose fp16: in [Z][R][C] -> out [Z][C][R]  (32x32 tiles through shared memory)
+__global__ void k_transpose(const __half* __restrict__ in, __half* __restrict__ out, int R, int C) {
+    __shared__ __half tile[32][34];
+    const size_t zoff = (size_t)blockIdx.z * R * C;
+    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) if (r0 + j < R && c < C) tile[j][threadIdx.x] = in[zoff + (size_t)(r0 + j) * C + c];
+    __syncthreads();
+    int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) if (c0 + j < C && r < R) out[zoff + (size_t)(c0 + j) * R + r] = tile[threadIdx.x][j];
+}
+// channel concat: out[p][0:Ca] = a[p], out[p][Ca:Ca+Cb] = b[p]   (8-channel vectors)
+__global__ void k_concat(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out, size_t pixels, int Ca, int Cb) {
+    const int va = Ca / 8, vb = Cb / 8, vt = va + vb;
+    const size_t total = pixels * vt;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i / vt; const int v = (int)(i % vt);
+        const uint4 val = v < va ? *reinterpret_cast<const uint4*>(a + (p * va + v) * 8) : *reinterpret_cast<const uint4*>(b + (p * vb + (v - va)) * 8);
+        *reinterpret_cast<uint4*>(out + i * 8) = val;
+    }
+}
+// nearest 2x upsample NHWC
+__global__ void k_upsample2x(const __half* __restrict__ in, __half* __restrict__ out, int N, int H, int W, int C) {
+    const int vc = C / 8;
+    const size_t total = (size_t)N * 2 * H * 2 * W * vc;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vc); size_t p = i / vc;
+        const int w = (int)(p % (2 * W)); p /= (2 * W); const int h = (int)(p % (2 * H)); const int n = (int)(p / (2 * H));
+        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(in + ((((size_t)n * H + h / 2) * W + w / 2) * vc + v) * 8);
+    }
+}
+// im2col for a 3x3 stride-2 conv: in [N,H,W,C] -> col [N*Ho*Wo][9*C]; pad_lo = 1 (symmetric pad 1, U-Net) or 0 (pad (0,1,0,1), VAE)
+__global__ void k_im2col_s2(const __half* __restrict__ in, __half* __restrict__ col, int N, int H, int W, int C, int Ho, int Wo, int pad_lo) {
+    const int vc = C / 8;
+    const size_t total = (size_t)N * Ho * Wo * 9 * vc;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vc); size_t r = i / vc;
+        const int tap = (int)(r % 9); r /= 9;
+        const int wo = (int)(r % Wo); r /= Wo; const int ho = (int)(r % Ho); const int n = (int)(r / Ho);
+        const int h = 2 * ho + tap / 3 - pad_lo, w = 2 * wo + tap % 3 - pad_lo;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (h >= 0 && h < H && w >= 0 && w < W) val = *reinterpret_cast<const uint4*>(in + ((((size_t)n * H + h) * W + w) * vc + v) * 8);
+        *reinterpret_cast<uint4*>(col + i * 8) = val;
+    }
+}
+// col2im (gather form) for the same conv: dx[n,h,w,c] = sum over (tap, ho, wo) with 2*ho + ky - pad == h ... of dcol[(n,ho,wo)][tap][c]
+__global__ void k_col2im_s2(const __half* __restrict__ dcol, __half* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo, int pad_lo) {
+    const int vc = C / 8;
+    const size_t total = (size_t)N * H * W * vc;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vc); size_t p = i / vc;
+        const int w = (int)(p % W); p /= W; const int h = (int)(p % H); const int n = (int)(p / H);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        #pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+            const int th = h + pad_lo - ky;
+            if (th < 0 || (th & 1)) continue;
+            const int ho = th >> 1; if (ho >= Ho) continue;
+            #pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const int tw = w + pad_lo - kx;
+                if (tw < 0 || (tw & 1)) continue;
+                const int wo = tw >> 1; if (wo >= Wo) continue;
+                const uint4 raw = *reinterpret_cast<const uint4*>(dcol + (((((size_t)n * Ho + ho) * Wo + wo) * 9 + ky * 3 + kx) * vc + v) * 8);
+                const __half* hh = reinterpret_cast<const __half*>(&raw);
+                #pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] += __half2float(hh[k]);
+            }
+        }
+        __align__(16) __half o[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = __float2half_rn(acc[k]);
+        *reinterpret_cast<uint4*>(dx + i * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+// dx[n,h,w] = sum of the 4 upsampled children (backward of nearest 2x) -- not needed by the frozen U-Net (no grad), kept out.
+
+// out = a + b (fp16, vectors of 8)
+__global__ void k_add(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out, size_t nvec) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 ra = *reinterpret_cast<const uint4*>(a + i * 8), rb = *reinterpret_cast<const uint4*>(b + i * 8);
+        const __half2* ha = reinterpret_cast<const __half2*>(&ra); const __half2* hb = reinterpret_cast<const __half2*>(&rb);
+        uint4 ro; __half2* ho = reinterpret_cast<__half2*>(&ro);
+        #pragma unroll
+        for (int k = 0; k < 4; k++) ho[k] = __hadd2(ha[k], hb[k]);
+        *reinterpret_cast<uint4*>(out + i * 8) = ro;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small direct 3x3 convolutions (stride 1, pad 1), NHWC.  Used where the channel count is too small for the
+// 64-wide K blocks of the tensor-core tiles: conv_in (Cin = 3 / 4), conv_out (Cout = 4 / 8) and their transposes.
+// ------------------------------------------------------------------------------------------------------------
+// small Cin (<= 8): thread per (pixel, cout); in fp16 [N,H,W,Cin], w fp32 [Cout][3][3][Cin] in shared, out fp16 [N,H,W,Cout]
+template <int CIN>
+__global__ void k_conv_small_cin(const __half* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ out,
+                                 int N, int H, int W, int Cout) {
+    extern __shared__ float sw[];                 // [Cout][9*CIN]
+    for (int i = threadIdx.x; i < Cout * 9 * CIN; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const size_t total = (size_t)N * H * W * Cout;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout); size_t p = i / Cout;
+        const int x = (int)(p % W); p /= W; const int y = (int)(p % H); const int n = (int)(p / H);
+        float acc = bias ? bias[co] : 0.f;
+        #pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+            const int yy = y + ky - 1; if (yy < 0 || yy >= H) continue;
+            #pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const int xx = x + kx - 1; if (xx < 0 || xx >= W) continue;
+                const __half* ip = in + (((size_t)n * H + yy) * W + xx) * CIN;
+                const float* wp = sw + (co * 9 + ky * 3 + kx) * CIN;
+                #pragma unroll
+                for (int c = 0; c < CIN; c++) acc = fmaf(__half2float(ip[c]), wp[c], acc);
+            }
+        }
+        out[i] = __float2half_rn(acc);
+    }
+}
+// small Cout (<= 8): warp per pixel, lanes split Cin (8 channels per lane step); w fp16 [Cout][3][3][Cin]; out fp32 [N,H,W,Cout]
+template <int COUT>
+__global__ void k_conv_small_cout(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                                  int N, int H, int W, int Cin) {
+    const size_t pix = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= (size_t)N * H * W) return;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+    float acc[COUT];
+    #pragma unroll
+    for (int o = 0; o < COUT; o++) acc[o] = 0.f;
+    for (int ky = 0; ky < 3; ky++) {
+        const int yy = y + ky - 1; if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 3; kx++) {
+            const int xx = x + kx - 1; if (xx < 0 || xx >= W) continue;
+            const __half* ip = in + (((size_t)n * H + yy) * W + xx) * Cin;
+            for (int c = lane * 8; c < Cin; c += 256) {
+                const uint4 ri = *reinterpret_cast<const uint4*>(ip + c);
+                const __half* hi = reinterpret_cast<const __half*>(&ri);
+                #pragma unroll
+                for (int o = 0; o < COUT; o++) {
+                    const uint4 rw = *reinterpret_cast<const uint4*>(w + ((size_t)(o * 9 + ky * 3 + kx)) * Cin + c);
+                    const __half* hw = reinterpret_cast<const __half*>(&rw);
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++) acc[o] = fmaf(__half2float(hi[k]), __half2float(hw[k]), acc[o]);
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int o = 0; o < COUT; o++) { acc[o] = warp_sum(acc[o]); }
+    if (lane == 0) {
+        #pragma unroll
+        for (int o = 0; o < COUT; o++) out[pix * COUT + o] = acc[o] + (bias ? bias[o] : 0.f);
+    }
+}
+
+// y[b][n] = bias[n] + sum_k act(x[b][k]) * W[n][k]   (B <= 8 rows; time embedding MLP and per-ResBlock temb projections)
+__global__ void k_linear_small(const float* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                               int B, int N, int K, int silu_in, int silu_out) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane * 8; k < K; k += 256) {
+        const uint4 rw = *reinterpret_cast<const uint4*>(w + (size_t)n * K + k);
+        const __half* hw = reinterpret_cast<const __half*>(&rw);
+        for (int b = 0; b < B; b++) {
+            #pragma unroll
+            for (int j = 0; j < 8; j++) { float v = x[(size_t)b * K + k + j]; if (silu_in) v = silu(v); acc[b] = fmaf(v, __half2float(hw[j]), acc[b]); }
+        }
+    }
+    for (int b = 0; b < B; b++) {
+        float v = warp_sum(acc[b]);
+        if (lane == 0) { v += bias ? bias[n] : 0.f; if (silu_out) v = silu(v); y[(size_t)b * N + n] = v; }
+    }
+}
+
+// sinusoidal timestep embedding (diffusers Timesteps, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos | sin]
+__global__ void k_time_proj(const long long* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, j = i % half;
+    const float freq = expf(-logf(10000.f) * (float)j / (float)half);
+    const float a = (float)t[0] * freq;
+    out[(size_t)b * dim + j] = cosf(a);
+    out[(size_t)b * dim + half + j] = sinf(a);
+}
+
+}  // namespace sdk

@@ -42,7 +42,8 @@ struct GemmParams {
     __half* out;                 // fp16 output or nullptr
     float* out_f32;              // fp32 output or nullptr
     long long ldc;               // row stride (elements) of out
-    long long out_batch_stride;  // elements between batches (blockIdx.z)
+    int out_z1;                  // blockIdx.z -> out offset (z % out_z1) * out_s_lo + (z / out_z1) * out_s_hi (elements)
+    long long out_s_lo, out_s_hi;
     const float* bias;           // [N] fp32 or nullptr
     const float* row_bias;       // [M / rows_per_group][N] fp32 (time-embedding term) or nullptr
     int rows_per_group;
@@ -235,6 +236,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int row = quarter * 32 + lane;               // accumulator row == tile row
         const int m = m_blk * BLOCK_M + row;
         const bool row_ok = m < p.m_valid;
+        const size_t zoff = (size_t)(z % p.out_z1) * p.out_s_lo + (size_t)(z / p.out_z1) * p.out_s_hi;
         const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(((long long)z * p.M + m) / p.rows_per_group) * p.N : nullptr;
         #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -252,7 +254,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             if (!row_ok) continue;
             if (p.epi_mode == EPI_GEGLU) {
                 // weight rows were interleaved (value, gate) at plan time: out[:, n/2] = value * gelu(gate)
-                __half* o = p.out + (size_t)z * p.out_batch_stride + (size_t)m * p.ldc + (n0 >> 1);
+                __half* o = p.out + zoff + (size_t)m * p.ldc + (n0 >> 1);
                 __align__(16) __half h[16];
                 #pragma unroll
                 for (int i = 0; i < 16; i++) h[i] = __float2half_rn(f[2 * i] * gelu_erf(f[2 * i + 1]));
@@ -260,12 +262,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(h + 8);
             } else if (p.epi_mode == EPI_TRANSPOSED) {
                 // out[z][n][m]: lanes hold consecutive m -> each store instruction writes 64 contiguous bytes per n
-                __half* o = p.out + (size_t)z * p.out_batch_stride + (size_t)n0 * p.ldc + m;
+                __half* o = p.out + zoff + (size_t)n0 * p.ldc + m;
                 #pragma unroll
                 for (int i = 0; i < 32; i++) o[(size_t)i * p.ldc] = __float2half_rn(f[i]);
             } else {
                 if (p.residual) {
-                    const __half* r = p.residual + (size_t)z * p.out_batch_stride + (size_t)m * p.ld_res + n0;
+                    const __half* r = p.residual + zoff + (size_t)m * p.ld_res + n0;
                     #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r) + q);
@@ -275,11 +277,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     }
                 }
                 if (p.out_f32) {
-                    float* o = p.out_f32 + (size_t)z * p.out_batch_stride + (size_t)m * p.ldc + n0;
+                    float* o = p.out_f32 + zoff + (size_t)m * p.ldc + n0;
                     #pragma unroll
                     for (int q = 0; q < 8; q++) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
                 } else {
-                    __half* o = p.out + (size_t)z * p.out_batch_stride + (size_t)m * p.ldc + n0;
+                    __half* o = p.out + zoff + (size_t)m * p.ldc + n0;
                     __align__(16) __half h[32];
                     #pragma unroll
                     for (int i = 0; i < 32; i++) h[i] = __float2half_rn(f[i]);

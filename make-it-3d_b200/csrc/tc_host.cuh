@@ -68,13 +68,13 @@ inline int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmPar
         MI3D_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmemBytes));
         attr = true;
     }
-    dim3 grid(p.M / BLOCK_M, p.N / BN, batch);
+    dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, p.N / BN, batch);
     k_tc_gemm<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, p);
     return (int)cudaGetLastError();
 }
 
 inline int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int block_n, int batch, cudaStream_t st) {
-    if (p.M % BLOCK_M || p.K % BLOCK_K || p.N % block_n) return MI3D_ERR_ARG;
+    if (p.K % BLOCK_K || p.N % block_n || p.out_z1 < 1) return MI3D_ERR_ARG;
     switch (block_n) {
         case 64: return launch_bn<64>(ma, mb, p, batch, st);
         case 128: return launch_bn<128>(ma, mb, p, batch, st);

@@ -20,7 +20,7 @@ int mi3d_gemm_f16(const void* a, const void* b, void* out, int out_is_f32, int M
     p.M = M; p.N = N; p.K = K; p.num_k_blocks = K / 64; p.conv = 0; p.a_z1 = 1; p.b_z1 = 1; p.b_batched = 0;
     p.out = out_is_f32 ? nullptr : (__half*)out; p.out_f32 = out_is_f32 ? (float*)out : nullptr;
     p.ldc = epi_mode == tc::EPI_GEGLU ? N / 2 : (epi_mode == tc::EPI_TRANSPOSED ? M : N);
-    p.out_batch_stride = 0; p.bias = bias; p.row_bias = nullptr; p.rows_per_group = 1;
+    p.out_z1 = 1; p.out_s_lo = 0; p.out_s_hi = 0; p.bias = bias; p.row_bias = nullptr; p.rows_per_group = 1;
     p.residual = (const __half*)residual; p.ld_res = N; p.epi_mode = epi_mode; p.alpha = alpha; p.m_valid = M;
     return tc::launch(ma, mb, p, block_n, 1, (cudaStream_t)stream);
 }
@@ -43,7 +43,7 @@ int mi3d_conv3x3_f16(const void* x, const void* w, void* y, int Nimg, int H, int
     p.M = (int)Mtot; p.N = Cout; p.K = 9 * Cin; p.num_k_blocks = 9 * (Cin / 64); p.conv = 1;
     p.conv_H = H; p.conv_W = W; p.conv_bw = bw; p.conv_bh = bh; p.cin_blocks = Cin / 64;
     p.a_z1 = 1; p.b_z1 = 1; p.b_batched = 0;
-    p.out = (__half*)y; p.out_f32 = nullptr; p.ldc = Cout; p.out_batch_stride = 0; p.bias = bias; p.row_bias = nullptr;
+    p.out = (__half*)y; p.out_f32 = nullptr; p.ldc = Cout; p.out_z1 = 1; p.out_s_lo = 0; p.out_s_hi = 0; p.bias = bias; p.row_bias = nullptr;
     p.rows_per_group = 1; p.residual = (const __half*)residual; p.ld_res = Cout; p.epi_mode = tc::EPI_PLAIN; p.alpha = 1.f;
     p.m_valid = (int)Mtot;
     return tc::launch(ma, mb, p, block_n, 1, (cudaStream_t)stream);

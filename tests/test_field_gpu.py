@@ -166,7 +166,11 @@ def test_full_size_properties_128():
     a = net.render(_cu(ro)[None], _cu(rd)[None], **kw)
     ws = list(net._workspaces.values())[0]
     total = int(ws.counter[0])
-    assert total == 424400                                            # oracle count for this camera (M ~ 0.42 M)
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    n_o, f_o = orm.near_far_from_aabb(ro, rd, aabb, 0.2)
+    *_, rays_o_, tot_o = orm.march_rays_train(ro, rd, 1.0, sphere_bitfield(0.2), 1, 128, n_o, f_o, noises, 0.0, 512, align=128)
+    assert total == tot_o and 400000 < total < 450000                 # oracle count (M ~ 0.42 M for this camera)
+    assert np.array_equal(ws.rays.cpu().numpy(), rays_o_)
     img, wsum = a["image"][0], a["weights_sum"][0]
     assert torch.isfinite(img).all() and (wsum >= 0).all() and (wsum <= 1 + 1e-5).all()
     # rays that miss every occupied cell return exactly the background and the far depth
