@@ -15,6 +15,22 @@ from torch.autograd import Function
 from .. import _lib as L
 
 
+# Optional live kernel timing (bench.py roofline leg): a list that receives (kernel_name, start_event, end_event, info) tuples,
+# recorded on the launching stream around the C-ABI call.  None = off (no events, no overhead).
+PROFILE = None
+
+
+def _timed(name, info, fn):
+    if PROFILE is None:
+        return fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    r = fn()
+    e.record()
+    PROFILE.append((name, s, e, info))
+    return r
+
+
 def make_hashgrid(n_levels=16, base_resolution=16, per_level_scale=1.3819128274917603, log2_hashmap_size=19):
     hg = L.HashGrid()
     L.check(L.lib().mi3d_hashgrid_make(C.c_uint32(n_levels), C.c_uint32(base_resolution), C.c_double(per_level_scale),
@@ -173,9 +189,10 @@ class _RenderTrain(Function):
         io.seed = opts["seed"] + 1
         mlp, cf = _mlp_struct(P), _cfg_struct(cfg, light_d)
         losses = torch.zeros(2, dtype=torch.float32, device=dev)
-        L.check(lib.mi3d_field_forward(C.byref(io), L.ptr(table), C.byref(hg), C.byref(mlp), C.byref(cf), L.ptr(ws.sigmas),
-                                       L.ptr(ws.rgbs), C.c_void_p(0), L.ptr(ws.tape), L.ptr(ws.partials),
-                                       C.c_void_p(losses.data_ptr()), C.c_void_p(losses.data_ptr() + 4), L.stream()), "field_forward")
+        _timed("k_field_fwd", dict(n_evals=cfg["n_evals"], N=N), lambda: L.check(lib.mi3d_field_forward(
+            C.byref(io), L.ptr(table), C.byref(hg), C.byref(mlp), C.byref(cf), L.ptr(ws.sigmas), L.ptr(ws.rgbs), C.c_void_p(0),
+            L.ptr(ws.tape), L.ptr(ws.partials), C.c_void_p(losses.data_ptr()), C.c_void_p(losses.data_ptr() + 4), L.stream()),
+            "field_forward"))
         ep = L.Epilogue()
         ep.bg_color = bg_color.data_ptr() if bg_color is not None else None
         ep.bg_scalar = 1.0
@@ -222,9 +239,10 @@ class _RenderTrain(Function):
         io.seed = ctx.io_seed
         mlp, cf, gm = _mlp_struct(P), _cfg_struct(ctx.cfg, light_d), _mlp_struct(g_P)
         g_lo, g_ls = _grad_or_none(g_lo), _grad_or_none(g_ls)
-        L.check(lib.mi3d_field_backward(C.byref(io), L.ptr(table), C.byref(ctx.hg), C.byref(mlp), C.byref(cf), L.ptr(ws.tape),
-                                        L.ptr(ws.g_sigmas), L.ptr(ws.g_rgbs), C.c_void_p(0), L.ptr(g_lo), L.ptr(g_ls), L.ptr(g_table),
-                                        C.byref(gm), L.stream()), "field_backward")
+        full = (g_lo is not None) or (g_ls is not None) or ctx.cfg["shading"] != "albedo"
+        _timed("k_field_bwd", dict(n_evals=ctx.cfg["n_evals"], N=N, full=full), lambda: L.check(lib.mi3d_field_backward(
+            C.byref(io), L.ptr(table), C.byref(ctx.hg), C.byref(mlp), C.byref(cf), L.ptr(ws.tape), L.ptr(ws.g_sigmas), L.ptr(ws.g_rgbs),
+            C.c_void_p(0), L.ptr(g_lo), L.ptr(g_ls), L.ptr(g_table), C.byref(gm), L.stream()), "field_backward"))
         return (g_table, *g_P) + (None,) * 13
 
 
