@@ -287,13 +287,14 @@ def run_ours(args):
 
 def cpu_baseline(args, steps=1):
     """The oracle port of the reference algorithm (oracle/: C ray-march + PyTorch fp32 field / U-Net / VAE) on the host cores.
-    Bounded sample: the FULL-size SD guidance step once + the render forward/backward on a 1/16 ray subset (32x32 of the 128x128
-    view, k = 13), extrapolated linearly in the ray count.  A reported baseline, not the target."""
+    Bounded sample: the FULL-size SD guidance step once + the render forward/backward on a 1/64 ray subset (16x16 rays spanning the
+    128x128 view's field of view, k = 13), extrapolated linearly in the ray count.  A reported baseline, not the target."""
     from oracle import field_ref as fr
     from oracle import sd_ref
-    torch.set_num_threads(os.cpu_count())
+    # more threads than ~32 make torch's CPU kernels slower on these many-core hosts (measured: 128 threads -> 30x slower)
+    torch.set_num_threads(min(32, os.cpu_count()))
     cores = torch.get_num_threads()
-    sub = 32
+    sub = 16
     pose = orbit_pose(1.25, 80.0, 170.0)
     focal = sub / (2 * math.tan(math.radians(20.0) / 2))
     ro, rd, sc = fr.get_rays_ref(pose, (focal, focal, sub / 2, sub / 2), sub, sub)
@@ -316,7 +317,7 @@ def cpu_baseline(args, steps=1):
                               torch.randn(1, 4, 64, 64, generator=g), guidance_scale=10.0)
     t_sd = time.time() - t0
     return {"value": round(1.0 / (t_render + t_sd), 5), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 full-size SD guidance step ({t_sd:.1f} s) + render fwd/bwd on a 32x32 ray subset extrapolated x16 ({t_render:.1f} s)"}
+            "sample": f"1 full-size SD guidance step ({t_sd:.1f} s) + render fwd/bwd on a 16x16 ray subset extrapolated x64 ({t_render:.1f} s extrapolated)"}
 
 
 def run_reference(args):

@@ -148,14 +148,16 @@ struct Engine {
         g.stats = (double*)alloc((size_t)x.n * g.G * 2 * sizeof(double));
         if (dry) return g;
         const int HW = x.h * x.w, C = x.c, G = g.G, N = x.n;
-        int chunks = (HW + 1023) / 1024; const int ppc = (HW + chunks - 1) / chunks;
+        const int VPP = C / 8, PL = std::max(1, 256 / VPP), threads = PL * VPP;
+        if (G > 64 || threads > 1024 || C % 8) { err = MI3D_ERR_ARG; return g; }
+        // enough CTAs to fill the machine twice, at least PL*8 pixels each
+        int chunks = std::max(1, std::min((HW + PL * 8 - 1) / (PL * 8), (2 * num_sms + N - 1) / N));
+        const int ppc = (HW + chunks - 1) / chunks; chunks = (HW + ppc - 1) / ppc;
         const __half* xp = x.p; __half* yp = y.p; const GN gg = g;
-        const size_t total_vec = x.numel() / 8;
         push([=](cudaStream_t st) {
             cudaMemsetAsync(gg.stats, 0, (size_t)N * G * 2 * sizeof(double), st);
-            sdk::k_gn_stats<<<dim3(chunks, N), 256, 2 * G * sizeof(float), st>>>(xp, HW, C, G, ppc, gg.stats);
-            const int blocks = (int)std::min<size_t>((total_vec + 255) / 256, 148 * 16);
-            sdk::k_gn_apply<<<blocks, 256, 0, st>>>(xp, yp, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, total_vec);
+            sdk::k_gn_stats<<<dim3(chunks, N), threads, 2 * C * sizeof(float), st>>>(xp, HW, C, G, ppc, gg.stats);
+            sdk::k_gn_apply<<<dim3(chunks, N), threads, 0, st>>>(xp, yp, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, ppc);
             return (int)cudaGetLastError();
         });
         return g;
@@ -165,13 +167,14 @@ struct Engine {
         double* bstats = (double*)alloc((size_t)g.x.n * g.G * 2 * sizeof(double));
         if (dry) return;
         const int HW = g.x.h * g.x.w, C = g.x.c, G = g.G, N = g.x.n;
-        int chunks = (HW + 1023) / 1024; const int ppc = (HW + chunks - 1) / chunks;
-        const size_t total_vec = g.x.numel() / 8; const GN gg = g;
+        const int VPP = C / 8, PL = std::max(1, 256 / VPP), threads = PL * VPP;
+        int chunks = std::max(1, std::min((HW + PL * 8 - 1) / (PL * 8), (2 * num_sms + N - 1) / N));
+        const int ppc = (HW + chunks - 1) / chunks; chunks = (HW + ppc - 1) / ppc;
+        const GN gg = g;
         push([=](cudaStream_t st) {
             cudaMemsetAsync(bstats, 0, (size_t)N * G * 2 * sizeof(double), st);
-            sdk::k_gn_bwd_stats<<<dim3(chunks, N), 256, 2 * G * sizeof(float), st>>>(gg.x.p, dy, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, ppc, bstats);
-            const int blocks = (int)std::min<size_t>((total_vec + 255) / 256, 148 * 16);
-            sdk::k_gn_bwd_apply<<<blocks, 256, 0, st>>>(gg.x.p, dy, gg.stats, bstats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, add, dx, total_vec);
+            sdk::k_gn_bwd_stats<<<dim3(chunks, N), threads, 2 * C * sizeof(float), st>>>(gg.x.p, dy, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, ppc, bstats);
+            sdk::k_gn_bwd_apply<<<dim3(chunks, N), threads, 0, st>>>(gg.x.p, dy, gg.stats, bstats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, add, dx, ppc);
             return (int)cudaGetLastError();
         });
     }

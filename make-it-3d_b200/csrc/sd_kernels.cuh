@@ -58,131 +58,165 @@ __global__ void k_geglu_w(const float* __restrict__ w, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// GroupNorm (+ SiLU) over NHWC fp16.  Pass 1: per-(n, group) sum / sum of squares in fp64 via block partials + atomics.
+// GroupNorm (+ SiLU) over NHWC fp16.
+// Thread mapping shared by all four kernels: blockDim = PL * VPP with VPP = C/8 channel vectors and PL pixel lanes;
+// thread (pl, cv) walks pixels p0+pl, p0+pl+PL, ... of image n = blockIdx.y and always sees the SAME 8 channels, so
+// per-channel partial sums live in registers; one shared-memory pass per CTA folds lanes -> channels -> groups and a
+// handful of fp64 atomics per CTA fold CTAs -> stats[n][g] = (sum, sum of squares).
 // ------------------------------------------------------------------------------------------------------------
-// grid (chunks, N); each CTA covers `pix_per_cta` pixels of image n; thread handles 8 channels of a pixel per iteration.
-__global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, int pix_per_cta, double* __restrict__ stats /*[N][G][2]*/) {
-    extern __shared__ float sm[];                 // [G][2]
-    const int n = blockIdx.y;
-    const int cpg = C / G;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    const int vec_per_pix = C / 8;
-    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
-    const size_t base = (size_t)n * HW * C;
-    // a vector of 8 channels spans at most two groups (cpg >= 4 here): accumulate both in registers per vector
-    for (long long i = (long long)p0 * vec_per_pix + threadIdx.x; i < (long long)p1 * vec_per_pix; i += blockDim.x) {
-        const int cv = (int)(i % vec_per_pix);
-        const uint4 raw = *reinterpret_cast<const uint4*>(x + base + (size_t)i * 8);
-        const __half* h = reinterpret_cast<const __half*>(&raw);
-        const int g0 = (cv * 8) / cpg;
-        if (cpg >= 8) {
-            float s0 = 0.f, ss0 = 0.f, s1 = 0.f, ss1 = 0.f;
-            #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const float v = __half2float(h[k]);
-                if ((cv * 8 + k) / cpg == g0) { s0 += v; ss0 += v * v; } else { s1 += v; ss1 += v * v; }
-            }
-            atomicAdd(&sm[2 * g0], s0); atomicAdd(&sm[2 * g0 + 1], ss0);
-            if ((cv * 8 + 7) / cpg != g0) { atomicAdd(&sm[2 * g0 + 2], s1); atomicAdd(&sm[2 * g0 + 3], ss1); }
-        } else {
-            #pragma unroll
-            for (int k = 0; k < 8; k++) { const float v = __half2float(h[k]); const int gg = (cv * 8 + k) / cpg; atomicAdd(&sm[2 * gg], v); atomicAdd(&sm[2 * gg + 1], v * v); }
-        }
+__device__ __forceinline__ void gn_group_consts(const double* __restrict__ stats, int n, int G, double cnt, float eps, float* sm_mean, float* sm_rstd) {
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const double m = stats[((size_t)n * G + g) * 2] / cnt;
+        const double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
+        sm_mean[g] = (float)m;
+        sm_rstd[g] = rsqrtf((float)(var > 0 ? var : 0) + eps);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(size_t)n * 2 * G + i], (double)sm[i]);
 }
 
-// y = act((x - mean) * rstd * gamma + beta); act = SiLU if silu != 0.  total = N*HW*C/8 vectors.
+__global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, int pix_per_cta, double* __restrict__ stats /*[N][G][2]*/) {
+    extern __shared__ float sm[];                 // [C][2]
+    const int n = blockIdx.y, cpg = C / G, VPP = C / 8, PL = blockDim.x / VPP;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int pl = threadIdx.x / VPP, cv = threadIdx.x % VPP;
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    float s[8], ss[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) { s[k] = 0.f; ss[k] = 0.f; }
+    if (pl < PL) {
+        const __half* base = x + ((size_t)n * HW) * C + (size_t)cv * 8;
+        for (int p = p0 + pl; p < p1; p += PL) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C));
+            const __half* h = reinterpret_cast<const __half*>(&raw);
+            #pragma unroll
+            for (int k = 0; k < 8; k++) { const float v = __half2float(h[k]); s[k] += v; ss[k] = fmaf(v, v, ss[k]); }
+        }
+        #pragma unroll
+        for (int k = 0; k < 8; k++) { atomicAdd(&sm[2 * (cv * 8 + k)], s[k]); atomicAdd(&sm[2 * (cv * 8 + k) + 1], ss[k]); }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double a = 0, b = 0;
+        for (int c = g * cpg; c < (g + 1) * cpg; c++) { a += sm[2 * c]; b += sm[2 * c + 1]; }
+        atomicAdd(&stats[((size_t)n * G + g) * 2], a); atomicAdd(&stats[((size_t)n * G + g) * 2 + 1], b);
+    }
+}
+
+// y = act((x - mean) * rstd * gamma + beta); same (chunks, N) grid and thread mapping as k_gn_stats
 __global__ void k_gn_apply(const __half* __restrict__ x, __half* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
-                           const float* __restrict__ beta, int HW, int C, int G, float eps, int do_silu, size_t total_vec) {
-    const int cpg = C / G, vec_per_pix = C / 8;
-    const double cnt = (double)HW * cpg;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % vec_per_pix);
-        const int n = (int)(i / ((size_t)vec_per_pix * HW));
-        const uint4 raw = *reinterpret_cast<const uint4*>(x + i * 8);
+                           const float* __restrict__ beta, int HW, int C, int G, float eps, int do_silu, int pix_per_cta) {
+    __shared__ float sm_mean[64], sm_rstd[64];
+    const int n = blockIdx.y, cpg = C / G, VPP = C / 8, PL = blockDim.x / VPP;
+    gn_group_consts(stats, n, G, (double)HW * cpg, eps, sm_mean, sm_rstd);
+    __syncthreads();
+    const int pl = threadIdx.x / VPP, cv = threadIdx.x % VPP;
+    if (pl >= PL) return;
+    float a[8], b[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = cv * 8 + k, g = c / cpg;
+        a[k] = sm_rstd[g] * gamma[c]; b[k] = beta[c] - sm_mean[g] * a[k];
+    }
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    const size_t base = ((size_t)n * HW) * C + (size_t)cv * 8;
+    for (int p = p0 + pl; p < p1; p += PL) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
         const __half* h = reinterpret_cast<const __half*>(&raw);
         __align__(16) __half o[8];
         #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const int c = cv * 8 + k, g = c / cpg;
-            const double m = stats[((size_t)n * G + g) * 2] / cnt;
-            const double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
-            const float rstd = rsqrtf((float)var + eps);
-            float v = (__half2float(h[k]) - (float)m) * rstd * gamma[c] + beta[c];
+            float v = fmaf(__half2float(h[k]), a[k], b[k]);
             if (do_silu) v = silu(v);
             o[k] = __float2half_rn(v);
         }
-        *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(y + base + (size_t)p * C) = *reinterpret_cast<const uint4*>(o);
     }
 }
 
-// GroupNorm(+SiLU) backward, pass 1: per-(n,group) sums of dz*gamma and dz*gamma*xhat (dz = dy * silu'(z) when do_silu)
+// GroupNorm(+SiLU) backward, pass 1: per-(n,group) sums of dg = dz*gamma and dg*xhat (dz = dy * silu'(z) when do_silu)
 __global__ void k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dy, const double* __restrict__ stats,
                                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G, float eps, int do_silu,
                                int pix_per_cta, double* __restrict__ bstats /*[N][G][2]*/) {
-    extern __shared__ float sm[];
-    const int n = blockIdx.y, cpg = C / G, vec_per_pix = C / 8;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+    extern __shared__ float sm[];                 // [C][2] then group constants
+    __shared__ float sm_mean[64], sm_rstd[64];
+    const int n = blockIdx.y, cpg = C / G, VPP = C / 8, PL = blockDim.x / VPP;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    gn_group_consts(stats, n, G, (double)HW * cpg, eps, sm_mean, sm_rstd);
     __syncthreads();
-    const double cnt = (double)HW * cpg;
-    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
-    const size_t base = (size_t)n * HW * C;
-    for (long long i = (long long)p0 * vec_per_pix + threadIdx.x; i < (long long)p1 * vec_per_pix; i += blockDim.x) {
-        const int cv = (int)(i % vec_per_pix);
-        const uint4 rx = *reinterpret_cast<const uint4*>(x + base + (size_t)i * 8);
-        const uint4 rd = *reinterpret_cast<const uint4*>(dy + base + (size_t)i * 8);
-        const __half* hx = reinterpret_cast<const __half*>(&rx); const __half* hd = reinterpret_cast<const __half*>(&rd);
+    const int pl = threadIdx.x / VPP, cv = threadIdx.x % VPP;
+    if (pl < PL) {
+        float mu[8], rs[8], ga[8], be[8], s1[8], s2[8];
         #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int c = cv * 8 + k, g = c / cpg;
-            const double m = stats[((size_t)n * G + g) * 2] / cnt;
-            const double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
-            const float rstd = rsqrtf((float)var + eps);
-            const float xh = (__half2float(hx[k]) - (float)m) * rstd;
-            float d = __half2float(hd[k]);
-            if (do_silu) d *= silu_grad(xh * gamma[c] + beta[c]);
-            const float dg = d * gamma[c];
-            atomicAdd(&sm[2 * g], dg); atomicAdd(&sm[2 * g + 1], dg * xh);
+            mu[k] = sm_mean[g]; rs[k] = sm_rstd[g]; ga[k] = gamma[c]; be[k] = beta[c]; s1[k] = 0.f; s2[k] = 0.f;
         }
+        const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+        const size_t base = ((size_t)n * HW) * C + (size_t)cv * 8;
+        for (int p = p0 + pl; p < p1; p += PL) {
+            const uint4 rx = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
+            const uint4 rd = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C));
+            const __half* hx = reinterpret_cast<const __half*>(&rx); const __half* hd = reinterpret_cast<const __half*>(&rd);
+            #pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float xh = (__half2float(hx[k]) - mu[k]) * rs[k];
+                float d = __half2float(hd[k]);
+                if (do_silu) d *= silu_grad(fmaf(xh, ga[k], be[k]));
+                const float dg = d * ga[k];
+                s1[k] += dg; s2[k] = fmaf(dg, xh, s2[k]);
+            }
+        }
+        #pragma unroll
+        for (int k = 0; k < 8; k++) { atomicAdd(&sm[2 * (cv * 8 + k)], s1[k]); atomicAdd(&sm[2 * (cv * 8 + k) + 1], s2[k]); }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&bstats[(size_t)n * 2 * G + i], (double)sm[i]);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double a = 0, b = 0;
+        for (int c = g * cpg; c < (g + 1) * cpg; c++) { a += sm[2 * c]; b += sm[2 * c + 1]; }
+        atomicAdd(&bstats[((size_t)n * G + g) * 2], a); atomicAdd(&bstats[((size_t)n * G + g) * 2 + 1], b);
+    }
 }
 // pass 2: dx = rstd * (dg - mean(dg) - xhat * mean(dg*xhat)) (+ add, optional accumulation of another gradient branch)
 __global__ void k_gn_bwd_apply(const __half* __restrict__ x, const __half* __restrict__ dy, const double* __restrict__ stats,
                                const double* __restrict__ bstats, const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
-                               int G, float eps, int do_silu, const __half* __restrict__ add, __half* __restrict__ dx, size_t total_vec) {
-    const int cpg = C / G, vec_per_pix = C / 8;
+                               int G, float eps, int do_silu, const __half* __restrict__ add, __half* __restrict__ dx, int pix_per_cta) {
+    __shared__ float sm_mean[64], sm_rstd[64], sm_m1[64], sm_m2[64];
+    const int n = blockIdx.y, cpg = C / G, VPP = C / 8, PL = blockDim.x / VPP;
     const double cnt = (double)HW * cpg;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % vec_per_pix);
-        const int n = (int)(i / ((size_t)vec_per_pix * HW));
-        const uint4 rx = *reinterpret_cast<const uint4*>(x + i * 8);
-        const uint4 rd = *reinterpret_cast<const uint4*>(dy + i * 8);
+    gn_group_consts(stats, n, G, cnt, eps, sm_mean, sm_rstd);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        sm_m1[g] = (float)(bstats[((size_t)n * G + g) * 2] / cnt); sm_m2[g] = (float)(bstats[((size_t)n * G + g) * 2 + 1] / cnt);
+    }
+    __syncthreads();
+    const int pl = threadIdx.x / VPP, cv = threadIdx.x % VPP;
+    if (pl >= PL) return;
+    float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int c = cv * 8 + k, g = c / cpg;
+        mu[k] = sm_mean[g]; rs[k] = sm_rstd[g]; ga[k] = gamma[c]; be[k] = beta[c]; m1[k] = sm_m1[g]; m2[k] = sm_m2[g];
+    }
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    const size_t base = ((size_t)n * HW) * C + (size_t)cv * 8;
+    for (int p = p0 + pl; p < p1; p += PL) {
+        const uint4 rx = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
+        const uint4 rd = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C));
         uint4 ra = make_uint4(0, 0, 0, 0);
-        if (add) ra = *reinterpret_cast<const uint4*>(add + i * 8);
+        if (add) ra = __ldg(reinterpret_cast<const uint4*>(add + base + (size_t)p * C));
         const __half* hx = reinterpret_cast<const __half*>(&rx); const __half* hd = reinterpret_cast<const __half*>(&rd);
         const __half* ha = reinterpret_cast<const __half*>(&ra);
         __align__(16) __half o[8];
         #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const int c = cv * 8 + k, g = c / cpg;
-            const double m = stats[((size_t)n * G + g) * 2] / cnt;
-            const double var = stats[((size_t)n * G + g) * 2 + 1] / cnt - m * m;
-            const float rstd = rsqrtf((float)var + eps);
-            const float xh = (__half2float(hx[k]) - (float)m) * rstd;
+            const float xh = (__half2float(hx[k]) - mu[k]) * rs[k];
             float d = __half2float(hd[k]);
-            if (do_silu) d *= silu_grad(xh * gamma[c] + beta[c]);
-            const float dg = d * gamma[c];
-            const float m1 = (float)(bstats[((size_t)n * G + g) * 2] / cnt), m2 = (float)(bstats[((size_t)n * G + g) * 2 + 1] / cnt);
-            float v = rstd * (dg - m1 - xh * m2);
+            if (do_silu) d *= silu_grad(fmaf(xh, ga[k], be[k]));
+            const float dg = d * ga[k];
+            float v = rs[k] * (dg - m1[k] - xh * m2[k]);
             if (add) v += __half2float(ha[k]);
             o[k] = __float2half_rn(v);
         }
-        *reinterpret_cast<uint4*>(dx + i * 8) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(dx + base + (size_t)p * C) = *reinterpret_cast<const uint4*>(o);
     }
 }
 

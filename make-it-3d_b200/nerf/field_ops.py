@@ -97,6 +97,7 @@ class _FieldEval(Function):
                                                L.ptr(rgbs), L.ptr(normals), L.ptr(tape), L.ptr(partials),
                                                C.c_void_p(losses.data_ptr()), C.c_void_p(losses.data_ptr() + 4), L.stream()),
                     "field_forward")
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(table, w1, b1, w2, b2, w3, b3, xyzs, dirs, light_d, smooth_noise, tape)
         ctx.hg, ctx.cfg, ctx.seed, ctx.m = hg, cfg, seed, m
         if normals is None:
@@ -205,6 +206,7 @@ class _RenderTrain(Function):
             C.c_float(opts["T_thresh"]), L.ptr(ws.ws_raw), L.ptr(ws.depth_raw), L.ptr(ws.image_raw), C.byref(ep), L.ptr(image),
             L.ptr(depth), L.stream()), "composite_rays_train_forward")
         weights_sum = ws.ws_raw.clone()
+        ctx.set_materialize_grads(False)        # unused outputs arrive as None -> the backward skips evaluations that get no gradient
         ctx.save_for_backward(table, w1, b1, w2, b2, w3, b3, light_d, smooth_noise, bg_color, depth_scale)
         ctx.ws, ctx.hg, ctx.cfg, ctx.opts, ctx.N, ctx.generation = ws, hg, cfg, opts, N, ws.generation
         ctx.io_seed = io.seed
