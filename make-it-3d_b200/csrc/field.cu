@@ -19,7 +19,9 @@
 // Grid: persistent, gridDim = 148 SMs x resident CTAs; the number of valid rows is read from device memory
 // (counter[0] written by mi3d_march_rays_train), so there is no host synchronisation between march and field.
 #include "mi3d_common.cuh"
+#include "tc_gemm.cuh"
 #include "../../include/mi3d.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -456,6 +458,341 @@ __global__ void __launch_bounds__(NT, 2) k_field_fwd(const FwdArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// forward, tensor-core variant: the three layer GEMMs run on tcgen05.mma (kind::tf32) with a 3-term split
+//   x = hi + lo (hi = tf32-rounded x):  A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo     (error ~2^-21, fp32-class)
+// so the finite-difference normals keep their accuracy while the MLP leaves the FFMA pipe.
+// CTA = 416 threads, one 128-sample tile at a time (persistent):
+//   warps 0-3   owners  : thread r owns sample r == TMEM lane r; epilogues (bias, ReLU, hi/lo split -> next A operand in
+//                         shared memory, UMMA K-major 128B-swizzle layout) and all per-sample math / outputs
+//   warps 4-11  encoders: hash-grid gathers for the NEXT evaluation while the MMA / epilogue chain of the current one runs
+//   warp 12     MMA     : one thread issues tcgen05.mma; accumulators D1 | D2 | D3 live in TMEM columns [0,64) [64,128) [128,144)
+// Hand-offs are mbarriers (count = arriving threads, or tcgen05.commit from the MMA thread).
+// ---------------------------------------------------------------------------------------------------------
+namespace ftc {
+constexpr int kThreads = 416;
+constexpr int kA1 = 128 * 32 * 4;             // one [128 x 32] fp32 tile = 16 KB
+constexpr uint32_t kTmemCols = 256;
+// smem carve (bytes): A1_hi, A1_lo, A2_hi[2], A2_lo[2], W1_hi, W1_lo, W2_hi[2], W2_lo[2], W3_hi[2], W3_lo[2], then misc
+constexpr int oA1H = 0, oA1L = oA1H + kA1, oA2H = oA1L + kA1, oA2L = oA2H + 2 * kA1;
+constexpr int oW1H = oA2L + 2 * kA1, oW1L = oW1H + 8192, oW2H = oW1L + 8192, oW2L = oW2H + 16384;
+constexpr int oW3H = oW2L + 16384, oW3L = oW3H + 4096, oMisc = oW3L + 4096;
+constexpr size_t kSmem = 1024 + oMisc + 1024;
+
+// byte offset of element (row, k) inside a K-major 128B-swizzled [rows x 32 fp32] tile (tile base 1024-aligned)
+__device__ __forceinline__ uint32_t sw_off(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(bar)) : "memory");
+}
+// D (+)= A[128 x 32*KB] . B[N x 32*KB]^T over hi/lo split tiles; a_hi/a_lo/b_hi/b_lo are smem addresses of the first K-block
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int kblocks,
+                                            uint32_t a_kb_stride, uint32_t b_kb_stride, uint32_t idesc) {
+    uint32_t acc = 0;
+    for (int kb = 0; kb < kblocks; kb++) {
+        const uint64_t dah = tc::make_sw128_desc(a_hi + kb * a_kb_stride), dal = tc::make_sw128_desc(a_lo + kb * a_kb_stride);
+        const uint64_t dbh = tc::make_sw128_desc(b_hi + kb * b_kb_stride), dbl = tc::make_sw128_desc(b_lo + kb * b_kb_stride);
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {           // 4 x (K = 8 tf32 = 32 B) per 128 B swizzle row
+            umma_tf32(tmem_d, dah + 2 * k, dbh + 2 * k, idesc, acc); acc = 1;
+            umma_tf32(tmem_d, dal + 2 * k, dbh + 2 * k, idesc, 1);
+            umma_tf32(tmem_d, dah + 2 * k, dbl + 2 * k, idesc, 1);
+        }
+    }
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+}  // namespace ftc
+
+__global__ void __launch_bounds__(ftc::kThreads, 1) k_field_fwd_tc(const FwdArgs a) {
+    using namespace ftc;
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    float* b1s = reinterpret_cast<float*>(sm + oMisc);          // 64
+    float* b2s = b1s + 64;                                      // 64
+    float* b3s = b2s + 64;                                      // 4 (+pad)
+    LevelSm* lv = reinterpret_cast<LevelSm*>(b3s + 8);          // 16 * 20 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oMisc + 896);   // a1_full, a1_empty, d1_full, a2_full, d2_full, a3_full, d3_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);       // [2][4] loss partials
+    uint64_t *a1_full = bars, *a1_empty = bars + 1, *d1_full = bars + 2, *a2_full = bars + 3, *d2_full = bars + 4, *a3_full = bars + 5, *d3_full = bars + 6;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- one-time setup: weights split hi/lo into UMMA B-operand tiles ([out][in] is already [N][K] K-major) ----
+    for (int i = tid; i < D_H * D_IN; i += kThreads) {           // W1 [64][32]
+        const int n = i / D_IN, k = i % D_IN; const float v = a.mlp.w1[i], h = tf32_hi(v);
+        *reinterpret_cast<float*>(sm + oW1H + sw_off(n, k)) = h; *reinterpret_cast<float*>(sm + oW1L + sw_off(n, k)) = v - h;
+    }
+    for (int i = tid; i < D_H * D_H; i += kThreads) {            // W2 [64][64] -> two K-blocks of [64 x 32]
+        const int n = i / D_H, k = i % D_H; const float v = a.mlp.w2[i], h = tf32_hi(v);
+        const uint32_t o = (k >> 5) * 8192 + sw_off(n, k & 31);
+        *reinterpret_cast<float*>(sm + oW2H + o) = h; *reinterpret_cast<float*>(sm + oW2L + o) = v - h;
+    }
+    for (int i = tid; i < 16 * D_H; i += kThreads) {             // W3 [4][64] zero-padded to N = 16 -> two K-blocks of [16 x 32]
+        const int n = i / D_H, k = i % D_H; const float v = n < D_OUT ? a.mlp.w3[n * D_H + k] : 0.f, h = tf32_hi(v);
+        const uint32_t o = (k >> 5) * 2048 + sw_off(n, k & 31);
+        *reinterpret_cast<float*>(sm + oW3H + o) = h; *reinterpret_cast<float*>(sm + oW3L + o) = v - h;
+    }
+    for (int i = tid; i < D_H; i += kThreads) { b1s[i] = a.mlp.b1[i]; b2s[i] = a.mlp.b2[i]; }
+    if (tid < D_OUT) b3s[tid] = a.mlp.b3[tid];
+    if (tid < 16) {
+        LevelSm L; const int l = tid;
+        if (l < (int)a.hg.n_levels) {
+            L.offset = a.hg.offsets[l]; L.size = a.hg.sizes[l]; L.res = a.hg.ress[l]; L.scale = a.hg.scales[l];
+            L.hashed = (uint64_t)L.res * L.res * L.res > (uint64_t)L.size ? 1u : 0u;
+        } else { L.offset = 0; L.size = 8; L.res = 2; L.scale = 1.f; L.hashed = 0; }
+        lv[l] = L;
+    }
+    if (tid == 0) {
+        tc::mbar_init(a1_full, 256); tc::mbar_init(a1_empty, 1); tc::mbar_init(d1_full, 1); tc::mbar_init(a2_full, 128);
+        tc::mbar_init(d2_full, 1); tc::mbar_init(a3_full, 128); tc::mbar_init(d3_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 12) tc::tmem_alloc(tmem_slot, kTmemCols);
+    tc::fence_proxy_async();                 // weight tiles were written through the generic proxy, UMMA reads through the async proxy
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t sbase = tc::smem_u32(sm);
+
+    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
+    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
+    const int n_evals = a.n_evals;
+    const float inv2b = 2.f * a.bound;
+    float acc_orient = 0.f, acc_smooth = 0.f;
+    uint32_t it = 0;                         // global evaluation counter -> mbarrier phase parity
+
+    if (warp < 4) {
+        // ================================ owners ================================
+        const int r = tid;
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
+        float light[3] = {0.f, 0.f, 0.f};
+        if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
+        for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+            const uint32_t row = tile * T + r;
+            const bool in_range = row < m_pad, real = row < M;
+            float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
+            if (real) {
+                x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2];
+                if (a.dirs) { d[0] = a.dirs[3 * (size_t)row]; d[1] = a.dirs[3 * (size_t)row + 1]; d[2] = a.dirs[3 * (size_t)row + 2]; }
+            }
+            if (n_evals > 7 && in_range) {
+                float z[3];
+                if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
+                else gauss_pair(a.seed, row, 1u, z);
+                #pragma unroll
+                for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
+            }
+            float sigma0 = 0.f, alb[3] = {0.f, 0.f, 0.f}, tapv[12];
+            #pragma unroll
+            for (int i = 0; i < 12; i++) tapv[i] = 0.f;
+            for (int e = 0; e < n_evals; e++, it++) {
+                const uint32_t par = it & 1;
+                // ---- epilogue 1: H1 = relu(D1 + b1) -> A2 (hi/lo) ----
+                tc::mbar_wait(d1_full, par);
+                tc::tc_fence_after();
+                #pragma unroll 1
+                for (int c0 = 0; c0 < D_H; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(lane_addr + (uint32_t)c0, v);
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        float h[4], l[4];
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) { const float t = fmaxf(__uint_as_float(v[4 * q + j]) + b1s[c0 + 4 * q + j], 0.f); h[j] = tf32_hi(t); l[j] = t - h[j]; }
+                        const uint32_t o = (c0 >> 5) * kA1 + sw_off(r, 4 * q);
+                        *reinterpret_cast<float4*>(sm + oA2H + o) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(sm + oA2L + o) = make_float4(l[0], l[1], l[2], l[3]);
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                mbar_arrive(a2_full);
+                // ---- epilogue 2: H2 = relu(D2 + b2) -> A3 (reuses the A2 tiles: layer-2 MMAs have retired) ----
+                tc::mbar_wait(d2_full, par);
+                tc::tc_fence_after();
+                #pragma unroll 1
+                for (int c0 = 0; c0 < D_H; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(lane_addr + 64u + (uint32_t)c0, v);
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        float h[4], l[4];
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) { const float t = fmaxf(__uint_as_float(v[4 * q + j]) + b2s[c0 + 4 * q + j], 0.f); h[j] = tf32_hi(t); l[j] = t - h[j]; }
+                        const uint32_t o = (c0 >> 5) * kA1 + sw_off(r, 4 * q);
+                        *reinterpret_cast<float4*>(sm + oA2H + o) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(sm + oA2L + o) = make_float4(l[0], l[1], l[2], l[3]);
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                mbar_arrive(a3_full);
+                // ---- epilogue 3: outputs ----
+                tc::mbar_wait(d3_full, par);
+                tc::tc_fence_after();
+                uint32_t o4[4];
+                tmem_ld4(lane_addr + 128u, o4);
+                tc::tc_fence_before();
+                float p[3];
+                eval_pos(e, x, xp, a.bound, p);
+                const float sg = expf(__uint_as_float(o4[0]) + b3s[0] + blob(p, a.blob_density, a.two_r2));
+                if (e == 0) {
+                    sigma0 = sg;
+                    #pragma unroll
+                    for (int c = 0; c < 3; c++) alb[c] = 1.f / (1.f + expf(-(__uint_as_float(o4[1 + c]) + b3s[1 + c])));
+                } else {
+                    #pragma unroll
+                    for (int i = 0; i < 12; i++) if (i == e - 1) tapv[i] = sg;
+                }
+            }
+            if (in_range) {
+                float col[3] = {alb[0], alb[1], alb[2]};
+                if (n_evals >= 7) {
+                    const float sp[3] = {tapv[0], tapv[2], tapv[4]}, sn[3] = {tapv[1], tapv[3], tapv[5]};
+                    const Normal nm = make_normal(sp, sn);
+                    if (lit) {
+                        const float ndl = (nm.n[0] * light[0] + nm.n[1] * light[1]) + nm.n[2] * light[2];
+                        const float lam = a.ratio + (1 - a.ratio) * fmaxf(ndl, 0.1f);
+                        if (a.shading == MI3D_SHADING_TEXTURELESS) { col[0] = col[1] = col[2] = lam; }
+                        else if (a.shading == MI3D_SHADING_NORMAL) { col[0] = (nm.n[0] + 1) / 2; col[1] = (nm.n[1] + 1) / 2; col[2] = (nm.n[2] + 1) / 2; }
+                        else { col[0] = alb[0] * lam; col[1] = alb[1] * lam; col[2] = alb[2] * lam; }
+                    }
+                    const float wgt = 1.f - expf(-sigma0);
+                    const float ndd = fmaxf((nm.n[0] * d[0] + nm.n[1] * d[1]) + nm.n[2] * d[2], 0.f);
+                    acc_orient += wgt * (ndd * ndd);
+                    if (n_evals > 7) {
+                        const float sp2[3] = {tapv[6], tapv[8], tapv[10]}, sn2[3] = {tapv[7], tapv[9], tapv[11]};
+                        const Normal np = make_normal(sp2, sn2);
+                        acc_smooth += (fabsf(nm.n[0] - np.n[0]) + fabsf(nm.n[1] - np.n[1])) + fabsf(nm.n[2] - np.n[2]);
+                    }
+                    if (a.normals) { a.normals[3 * (size_t)row] = nm.n[0]; a.normals[3 * (size_t)row + 1] = nm.n[1]; a.normals[3 * (size_t)row + 2] = nm.n[2]; }
+                }
+                a.sigmas[row] = sigma0;
+                if (a.rgbs) { a.rgbs[3 * (size_t)row] = col[0]; a.rgbs[3 * (size_t)row + 1] = col[1]; a.rgbs[3 * (size_t)row + 2] = col[2]; }
+                if (a.tape) {
+                    float4* tp = reinterpret_cast<float4*>(a.tape + 16 * (size_t)row);
+                    tp[0] = make_float4(sigma0, alb[0], alb[1], alb[2]);
+                    tp[1] = make_float4(tapv[0], tapv[1], tapv[2], tapv[3]);
+                    tp[2] = make_float4(tapv[4], tapv[5], tapv[6], tapv[7]);
+                    tp[3] = make_float4(tapv[8], tapv[9], tapv[10], tapv[11]);
+                }
+            }
+        }
+    } else if (warp < 12) {
+        // ================================ encoders ================================
+        const int et = tid - 128, r = et & (T - 1), half = et >> 7;
+        const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
+        for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+            const uint32_t row = tile * T + r;
+            const bool in_range = row < m_pad, real = row < M;
+            float x[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
+            if (real) { x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2]; }
+            if (n_evals > 7 && in_range) {
+                float z[3];
+                if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
+                else gauss_pair(a.seed, row, 1u, z);
+                #pragma unroll
+                for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
+            }
+            for (int e = 0; e < n_evals; e++, it++) {
+                float p[3];
+                eval_pos(e, x, xp, a.bound, p);
+                const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
+                // gather first (registers), then wait for the A1 buffer to be released by the previous evaluation's layer-1 MMAs
+                float f[16];
+                #pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; continue; }
+                    const LevelSm L = lv[l0 + i];
+                    const CellW cw = hg_cell(u0, u1, u2, L.scale);
+                    const float2* __restrict__ base = reinterpret_cast<const float2*>(a.table) + L.offset;
+                    float2 v[8];
+                    #pragma unroll
+                    for (int corner = 0; corner < 8; corner++) {
+                        const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
+                        v[corner] = __ldg(base + hg_index(cx, cy, cz, L));
+                    }
+                    float f0 = 0.f, f1 = 0.f;
+                    #pragma unroll
+                    for (int corner = 0; corner < 8; corner++) {
+                        const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
+                        const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
+                        const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
+                        const float wt = wx * wy * wz;
+                        f0 = fmaf(wt, v[corner].x, f0); f1 = fmaf(wt, v[corner].y, f1);
+                    }
+                    f[2 * i] = f0; f[2 * i + 1] = f1;
+                }
+                if (it > 0) tc::mbar_wait(a1_empty, (it - 1) & 1);
+                #pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (i >= lcount) continue;
+                    const int k = 2 * (l0 + i);
+                    const float h0 = tf32_hi(f[2 * i]), h1 = tf32_hi(f[2 * i + 1]);
+                    const uint32_t o = sw_off(r, k);
+                    *reinterpret_cast<float2*>(sm + oA1H + o) = make_float2(h0, h1);
+                    *reinterpret_cast<float2*>(sm + oA1L + o) = make_float2(f[2 * i] - h0, f[2 * i + 1] - h1);
+                }
+                tc::fence_proxy_async();
+                mbar_arrive(a1_full);
+            }
+        }
+    } else {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t id64 = idesc_tf32(128, 64), id16 = idesc_tf32(128, 16);
+            for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+                for (int e = 0; e < n_evals; e++, it++) {
+                    const uint32_t par = it & 1;
+                    tc::mbar_wait(a1_full, par);
+                    tc::tc_fence_after();
+                    issue_layer(tmem, sbase + oA1H, sbase + oA1L, sbase + oW1H, sbase + oW1L, 1, kA1, 8192, id64);
+                    tc::umma_commit(a1_empty);
+                    tc::umma_commit(d1_full);
+                    tc::mbar_wait(a2_full, par);
+                    tc::tc_fence_after();
+                    issue_layer(tmem + 64u, sbase + oA2H, sbase + oA2L, sbase + oW2H, sbase + oW2L, 2, kA1, 8192, id64);
+                    tc::umma_commit(d2_full);
+                    tc::mbar_wait(a3_full, par);
+                    tc::tc_fence_after();
+                    issue_layer(tmem + 128u, sbase + oA2H, sbase + oA2L, sbase + oW3H, sbase + oW3L, 2, kA1, 2048, id16);
+                    tc::umma_commit(d3_full);
+                }
+            }
+        }
+    }
+    // ---- loss partials (owners only hold non-zero accumulators) + teardown ----
+    {
+        float v0 = acc_orient, v1 = acc_smooth;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+        if (warp < 4 && lane == 0) { red[warp] = v0; red[4 + warp] = v1; }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0 && a.loss_partials) {
+        a.loss_partials[2 * blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+        a.loss_partials[2 * blockIdx.x + 1] = (red[4] + red[5]) + (red[6] + red[7]);
+    }
+    if (warp == 12) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, kTmemCols); }
+}
+
 // loss_orient = sum / m_pad ; loss_smooth = sum / (3 m_pad)   (renderer.py:517-518, 523-524: .mean() over the padded rows)
 __global__ void k_loss_finalize(const float* __restrict__ partials, int n_part, const int* __restrict__ counter, uint32_t m_fixed,
                                 uint32_t align, uint32_t cap, float* __restrict__ loss_orient, float* __restrict__ loss_smooth) {
@@ -768,6 +1105,7 @@ int ensure_attrs() {
     if (!g_attr_set) {
         MI3D_CHECK(cudaFuncSetAttribute(k_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false)));
         MI3D_CHECK(cudaFuncSetAttribute(k_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true)));
+        MI3D_CHECK(cudaFuncSetAttribute(k_field_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftc::kSmem));
         g_attr_set = true;
     }
     return MI3D_OK;
@@ -811,6 +1149,9 @@ int mi3d_hashgrid_backward(const float* x, uint32_t E, const float* grad_out, co
     MI3D_RETURN_LAUNCH();
 }
 
+// MI3D_FIELD_TC=0 selects the FFMA forward kernel (kept for A/B measurements); default is the tcgen05 3xTF32 kernel
+static bool use_tc() { static int v = -1; if (v < 0) { const char* e = getenv("MI3D_FIELD_TC"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
+
 int mi3d_field_grid_ctas(int backward) { return num_sms() * (backward ? 1 : 2); }
 
 int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
@@ -828,8 +1169,9 @@ int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_h
     a.n_evals = cfg->n_evals; a.shading = cfg->shading; a.ratio = cfg->ambient_ratio; a.light_d = cfg->light_d;
     a.smooth_noise = io->smooth_noise; a.seed = io->seed;
     a.sigmas = sigmas; a.rgbs = rgbs; a.normals = normals; a.tape = tape; a.loss_partials = loss_partials;
-    const int grid = mi3d_field_grid_ctas(0);
-    k_field_fwd<<<grid, NT, smem_bytes(false), (cudaStream_t)stream>>>(a);
+    int grid = mi3d_field_grid_ctas(0);
+    if (use_tc()) { grid = num_sms(); k_field_fwd_tc<<<grid, ftc::kThreads, ftc::kSmem, (cudaStream_t)stream>>>(a); }
+    else k_field_fwd<<<grid, NT, smem_bytes(false), (cudaStream_t)stream>>>(a);
     if (loss_orient || loss_smooth)
         k_loss_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partials, grid, io->counter, io->m_fixed, io->align, io->cap, loss_orient, loss_smooth);
     MI3D_RETURN_LAUNCH();
