@@ -245,6 +245,10 @@ int mi3d_sd_unet_sds(mi3d_sd_t h, const float* latents, const float* noise, cons
 /* debug tap: device pointer + size of a named intermediate ("unet.mid", "vae.grad_in", ...) */
 int mi3d_sd_debug_tensor(mi3d_sd_t h, const char* name, void** ptr, size_t* bytes);
 
+/* unit-test entry for the hand-written kind::tf32 tiles of the field kernels (3-term split, K-major / MN-major operands):
+ * mode 0: d[128,N] = a[128,K] . b[N,K]^T ; mode 1: d = a[K,128]^T . b[K,N] ; mode 2: d = a[128,K] . b[K,N].  fp32 in/out. */
+int mi3d_tf32_tile_test(const float* a, const float* b, float* d, int N, int K, int mode, mi3d_stream_t stream);
+
 const char* mi3d_version(void);
 
 #ifdef __cplusplus

@@ -19,7 +19,7 @@
 // Grid: persistent, gridDim = 148 SMs x resident CTAs; the number of valid rows is read from device memory
 // (counter[0] written by mi3d_march_rays_train), so there is no host synchronisation between march and field.
 #include "mi3d_common.cuh"
-#include "tc_gemm.cuh"
+#include "tf32_tile.cuh"
 #include "../../include/mi3d.h"
 #include <stdlib.h>
 
@@ -469,7 +469,8 @@ __global__ void __launch_bounds__(NT, 2) k_field_fwd(const FwdArgs a) {
 //   warp 12     MMA     : one thread issues tcgen05.mma; accumulators D1 | D2 | D3 live in TMEM columns [0,64) [64,128) [128,144)
 // Hand-offs are mbarriers (count = arriving threads, or tcgen05.commit from the MMA thread).
 // ---------------------------------------------------------------------------------------------------------
-namespace ftc {
+namespace fwdtc {
+using namespace ::ftc;
 constexpr int kThreads = 416;
 constexpr int kA1 = 128 * 32 * 4;             // one [128 x 32] fp32 tile = 16 KB
 constexpr uint32_t kTmemCols = 256;
@@ -479,23 +480,6 @@ constexpr int oW1H = oA2L + 2 * kA1, oW1L = oW1H + 8192, oW2H = oW1L + 8192, oW2
 constexpr int oW3H = oW2L + 16384, oW3L = oW3H + 4096, oMisc = oW3L + 4096;
 constexpr size_t kSmem = 1024 + oMisc + 1024;
 
-// byte offset of element (row, k) inside a K-major 128B-swizzled [rows x 32 fp32] tile (tile base 1024-aligned)
-__device__ __forceinline__ uint32_t sw_off(int row, int k) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
-}
-__device__ __forceinline__ float tf32_hi(float x) {
-    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
-}
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(bar)) : "memory");
-}
 // D (+)= A[128 x 32*KB] . B[N x 32*KB]^T over hi/lo split tiles; a_hi/a_lo/b_hi/b_lo are smem addresses of the first K-block
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int kblocks,
                                             uint32_t a_kb_stride, uint32_t b_kb_stride, uint32_t idesc) {
@@ -511,14 +495,10 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint
         }
     }
 }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-}  // namespace ftc
+}  // namespace fwdtc
 
-__global__ void __launch_bounds__(ftc::kThreads, 1) k_field_fwd_tc(const FwdArgs a) {
-    using namespace ftc;
+__global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdArgs a) {
+    using namespace fwdtc;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     float* b1s = reinterpret_cast<float*>(sm + oMisc);          // 64
@@ -1105,7 +1085,7 @@ int ensure_attrs() {
     if (!g_attr_set) {
         MI3D_CHECK(cudaFuncSetAttribute(k_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false)));
         MI3D_CHECK(cudaFuncSetAttribute(k_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true)));
-        MI3D_CHECK(cudaFuncSetAttribute(k_field_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ftc::kSmem));
+        MI3D_CHECK(cudaFuncSetAttribute(k_field_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwdtc::kSmem));
         g_attr_set = true;
     }
     return MI3D_OK;
@@ -1170,7 +1150,7 @@ int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_h
     a.smooth_noise = io->smooth_noise; a.seed = io->seed;
     a.sigmas = sigmas; a.rgbs = rgbs; a.normals = normals; a.tape = tape; a.loss_partials = loss_partials;
     int grid = mi3d_field_grid_ctas(0);
-    if (use_tc()) { grid = num_sms(); k_field_fwd_tc<<<grid, ftc::kThreads, ftc::kSmem, (cudaStream_t)stream>>>(a); }
+    if (use_tc()) { grid = num_sms(); k_field_fwd_tc<<<grid, fwdtc::kThreads, fwdtc::kSmem, (cudaStream_t)stream>>>(a); }
     else k_field_fwd<<<grid, NT, smem_bytes(false), (cudaStream_t)stream>>>(a);
     if (loss_orient || loss_smooth)
         k_loss_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partials, grid, io->counter, io->m_fixed, io->align, io->cap, loss_orient, loss_smooth);

@@ -1,0 +1,65 @@
+// tf32_tile.cuh -- helpers for hand-written tcgen05 kind::tf32 tiles with a 3-term hi/lo split (fp32-class accuracy):
+//   x = hi + lo (hi = tf32-rounded x):  A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo
+// Storage convention for every operand tile: column blocks of [rows][32 fp32] (128-byte rows, 8-row / 1024-byte swizzle
+// atoms, block stride = rows * 128 B), written by ordinary threads through sw_off().  The SAME storage serves two uses:
+//   K-major  operand: rows = M or N index, columns = K   (descriptor: SBO = 1024 B, K advances by +32 B inside the row)
+//   MN-major operand: rows = K index,      columns = M/N (descriptor: LBO = block stride, SBO = 1024 B, K advances by +1024 B)
+// (cute::UMMA canonical layouts  K-major ((8,n),2):((8,SBO),1)  and  MN-major ((8,n),(8,k)):((1,LBO),(8,SBO)), in 16-byte units.)
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace ftc {
+
+// byte offset of element (row, k) inside one [rows x 32 fp32] block (block base 1024-aligned)
+__device__ __forceinline__ uint32_t sw_off(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + ((k & 3) << 2));
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+}
+// cute::UMMA::InstrDescriptor, kind::tf32: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, a_major @15, b_major @16 (1 = MN-major)
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// SW128 descriptor with an explicit leading-dimension byte offset (MN-major: distance between 32-element column blocks)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One operand = (hi base, lo base) of its first block + how to walk it.
+struct Operand { uint32_t hi, lo; uint32_t blk_stride; int mn_major; };
+
+// D[128 x N] (+)= A . B over K elements with the 3-term split.  K-major operands walk K as (block, +32 B); MN-major operands as (+1024 B).
+// `acc` in: 0 -> the first MMA overwrites D.  Returns 1.
+__device__ __forceinline__ uint32_t issue_3tf32(uint32_t tmem_d, const Operand& A, const Operand& B, int K, uint32_t idesc, uint32_t acc) {
+    for (int k8 = 0; k8 < K / 8; k8++) {
+        const uint32_t oa = A.mn_major ? (uint32_t)k8 * 1024u : (uint32_t)(k8 >> 2) * A.blk_stride + (uint32_t)(k8 & 3) * 32u;
+        const uint32_t ob = B.mn_major ? (uint32_t)k8 * 1024u : (uint32_t)(k8 >> 2) * B.blk_stride + (uint32_t)(k8 & 3) * 32u;
+        const uint32_t la = A.mn_major ? A.blk_stride : 16u, lb = B.mn_major ? B.blk_stride : 16u;
+        const uint64_t dah = desc_sw128(A.hi + oa, la), dal = desc_sw128(A.lo + oa, la);
+        const uint64_t dbh = desc_sw128(B.hi + ob, lb), dbl = desc_sw128(B.lo + ob, lb);
+        umma_tf32(tmem_d, dah, dbh, idesc, acc); acc = 1;
+        umma_tf32(tmem_d, dal, dbh, idesc, 1);
+        umma_tf32(tmem_d, dah, dbl, idesc, 1);
+    }
+    return acc;
+}
+
+}  // namespace ftc

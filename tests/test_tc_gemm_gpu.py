@@ -75,3 +75,21 @@ def test_implicit_conv3x3_matches_fp32_reference(L, Nimg, H, W, Cin, Cout):
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
     err = (y.float() - ref).abs().max().item()
     assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("N,K", [(64, 32), (64, 64), (32, 64), (16, 64), (64, 128), (32, 128)])
+def test_tf32_split_tiles(L, mode, N, K):
+    """Hand-written kind::tf32 tiles (field kernels): 3-term split must be fp32-class; K-major and MN-major descriptors."""
+    g = torch.Generator(device="cuda").manual_seed(N + K + mode)
+    if mode == 0:
+        a = torch.randn(128, K, device="cuda", generator=g); b = torch.randn(N, K, device="cuda", generator=g); ref = a.double() @ b.double().t()
+    elif mode == 1:
+        a = torch.randn(K, 128, device="cuda", generator=g); b = torch.randn(K, N, device="cuda", generator=g); ref = a.double().t() @ b.double()
+    else:
+        a = torch.randn(128, K, device="cuda", generator=g); b = torch.randn(K, N, device="cuda", generator=g); ref = a.double() @ b.double()
+    d = torch.empty(128, N, device="cuda")
+    L.check(L.lib().mi3d_tf32_tile_test(L.ptr(a), L.ptr(b), L.ptr(d), C.c_int(N), C.c_int(K), C.c_int(mode), L.stream()), "tf32_tile_test")
+    torch.cuda.synchronize()
+    err = (d.double() - ref).abs().max().item()
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), (mode, N, K, err)     # plain tf32 would be ~1e-2
