@@ -187,6 +187,9 @@ int mi3d_gemm_f16(const void* a, const void* b, void* out, int out_is_f32, int M
 
 /* Implicit-GEMM 3x3 stride-1 pad-1 convolution on the same kernel (stands in for the cuDNN conv under diffusers'
  * ResnetBlock2D / Downsample2D / Upsample2D): x [N,H,W,Cin] fp16 NHWC, w [Cout][3][3][Cin] fp16, y [N,H,W,Cout] fp16. */
+/* test path: out[M,N] (fp32) = A[M,K] . Bt[K,N], B consumed as an MN-major UMMA operand */
+int mi3d_gemm_f16_bt(const void* a, const void* bt, void* out, int M, int N, int K, int block_n, mi3d_stream_t stream);
+
 int mi3d_conv3x3_f16(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, int block_n,
                      const float* bias, const void* residual, mi3d_stream_t stream);
 

@@ -799,55 +799,10 @@ struct BwdArgs {
     float* g_table; mi3d_mlp_grad g_mlp;
 };
 
-__global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
-    extern __shared__ __align__(16) float smem_raw[];
-    const Smem s = carve(smem_raw, true);
-    load_weights(s, a.mlp, a.hg, true);
-    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
-    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
-    const int lrow = threadIdx.x & (T - 1), half = threadIdx.x >> 7;
-    const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
-    const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
-    float light[3] = {0.f, 0.f, 0.f};
-    if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
-    const float Go = (a.g_loss_orient && a.n_evals >= 7) ? *a.g_loss_orient / (float)m_pad : 0.f;
-    const float Gs = (a.g_loss_smooth && a.n_evals > 7) ? *a.g_loss_smooth / (3.f * (float)m_pad) : 0.f;
-    // which evaluations can receive a non-zero gradient (CTA-uniform)
-    const bool need_ptaps = Gs != 0.f;
-    const bool need_taps = a.n_evals >= 7 && (need_ptaps || Go != 0.f || lit || a.g_normals != nullptr);
-    const int e_end = !need_taps ? 1 : (need_ptaps ? 13 : 7);
-
-    float aw2[4][4], aw1[4][2], aw3 = 0.f, ab2[4], ab1[4], ab3 = 0.f;
-    #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        ab2[i] = 0.f; ab1[i] = 0.f;
-        #pragma unroll
-        for (int j = 0; j < 4; j++) aw2[i][j] = 0.f;
-        aw1[i][0] = 0.f; aw1[i][1] = 0.f;
-    }
-    __syncthreads();
-
-    for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
-        const uint32_t row = tile * T + lrow;
-        const bool in_range = row < m_pad, real = row < M;
-        float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
-        if (real) {
-            x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2];
-            if (a.dirs) { d[0] = a.dirs[3 * (size_t)row]; d[1] = a.dirs[3 * (size_t)row + 1]; d[2] = a.dirs[3 * (size_t)row + 2]; }
-        }
-        if (a.n_evals > 7 && in_range) {
-            float z[3];
-            if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
-            else gauss_pair(a.seed, row, 1u, z);
-            #pragma unroll
-            for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
-        }
-        // ---- per-sample output gradients (threads of half 0 own a sample) ----
-        float dh[4] = {0.f, 0.f, 0.f, 0.f};     // d/d(h0..h3) of the centre evaluation
-        float dtap[12];                          // d/d(h0) of the 12 tap evaluations
-        #pragma unroll
-        for (int i = 0; i < 12; i++) dtap[i] = 0.f;
-        if (half == 0 && in_range) {
+// d(loss)/d(h) of the 13 evaluations of one sample from the upstream gradients and the forward tape (sigma0, albedo, tap sigmas):
+// shading / orientation / smoothness -> normals -> finite differences -> tap densities -> trunc_exp / sigmoid pre-activations.
+__device__ __forceinline__ void sample_out_grads(const BwdArgs& a, uint32_t row, bool real, const float (&d)[3], bool lit, const float (&light)[3],
+                                                 float Go, float Gs, bool need_ptaps, float (&dh)[4], float (&dtap)[12]) {
             const float4* tp = reinterpret_cast<const float4*>(a.tape + 16 * (size_t)row);
             const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
             const float sigma0 = t0.x, alb[3] = {t0.y, t0.z, t0.w};
@@ -913,7 +868,57 @@ __global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
             dh[0] = gs * fminf(sigma0, 3269017.372472110639f);       // activation.py:12-16
             #pragma unroll
             for (int c = 0; c < 3; c++) dh[1 + c] = dalb[c] * alb[c] * (1.f - alb[c]);
+}
+
+__global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const Smem s = carve(smem_raw, true);
+    load_weights(s, a.mlp, a.hg, true);
+    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
+    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
+    const int lrow = threadIdx.x & (T - 1), half = threadIdx.x >> 7;
+    const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
+    const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
+    float light[3] = {0.f, 0.f, 0.f};
+    if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
+    const float Go = (a.g_loss_orient && a.n_evals >= 7) ? *a.g_loss_orient / (float)m_pad : 0.f;
+    const float Gs = (a.g_loss_smooth && a.n_evals > 7) ? *a.g_loss_smooth / (3.f * (float)m_pad) : 0.f;
+    // which evaluations can receive a non-zero gradient (CTA-uniform)
+    const bool need_ptaps = Gs != 0.f;
+    const bool need_taps = a.n_evals >= 7 && (need_ptaps || Go != 0.f || lit || a.g_normals != nullptr);
+    const int e_end = !need_taps ? 1 : (need_ptaps ? 13 : 7);
+
+    float aw2[4][4], aw1[4][2], aw3 = 0.f, ab2[4], ab1[4], ab3 = 0.f;
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ab2[i] = 0.f; ab1[i] = 0.f;
+        #pragma unroll
+        for (int j = 0; j < 4; j++) aw2[i][j] = 0.f;
+        aw1[i][0] = 0.f; aw1[i][1] = 0.f;
+    }
+    __syncthreads();
+
+    for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+        const uint32_t row = tile * T + lrow;
+        const bool in_range = row < m_pad, real = row < M;
+        float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
+        if (real) {
+            x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2];
+            if (a.dirs) { d[0] = a.dirs[3 * (size_t)row]; d[1] = a.dirs[3 * (size_t)row + 1]; d[2] = a.dirs[3 * (size_t)row + 2]; }
         }
+        if (a.n_evals > 7 && in_range) {
+            float z[3];
+            if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
+            else gauss_pair(a.seed, row, 1u, z);
+            #pragma unroll
+            for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
+        }
+        // ---- per-sample output gradients (threads of half 0 own a sample) ----
+        float dh[4] = {0.f, 0.f, 0.f, 0.f};     // d/d(h0..h3) of the centre evaluation
+        float dtap[12];                          // d/d(h0) of the 12 tap evaluations
+        #pragma unroll
+        for (int i = 0; i < 12; i++) dtap[i] = 0.f;
+        if (half == 0 && in_range) sample_out_grads(a, row, real, d, lit, light, Go, Gs, need_ptaps, dh, dtap);
 
         for (int e = 0; e < e_end; e++) {
             float p[3];
@@ -971,6 +976,418 @@ __global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
         atomicAdd(a.g_mlp.w3 + o * D_H + i, aw3);
         if (i == 0) atomicAdd(a.g_mlp.b3 + o, ab3);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward, tensor-core variant.  Same roles as k_field_fwd_tc; per evaluation the MMA thread runs
+//   F1: D1 = Enc W1^T          F2: D2 = H1 W2^T                               (recompute, K-major operands)
+//   G2: dH1 = dZ2 W2           WG2: dW2 += dZ2^T H1   (A3/A2/W2 tiles re-read MN-major: no transposed copies)
+//   G1: dEnc = dZ1 W1          WG1: dW1 += dZ1^T Enc
+// all as 3-term tf32 splits.  dW2 / dW1 accumulate in TMEM across the whole persistent CTA (M = 128 with the upper 64 rows
+// unused) and are flushed once at the end.  dZ3 -> dH2 (K = 4) and dW3 / db3 stay on the owner threads; db2 / db1 are column
+// sums of the dZ tiles taken by the encoder warps, which also read dEnc straight from TMEM and scatter it (RED.v2.f32).
+// TMEM columns: D1 [0,64) D2 [64,128) dH1 [128,192) dEnc [192,224) dW2 [256,320) dW1 [320,352).
+// ---------------------------------------------------------------------------------------------------------
+namespace bwdtc {
+using namespace ::ftc;
+constexpr int kThreads = 416;
+constexpr int kBlk = 128 * 32 * 4;             // one [128 x 32] fp32 block = 16 KB
+constexpr uint32_t kTmemCols = 512;
+constexpr int oA1H = 0, oA1L = oA1H + kBlk;                       // Enc           [128 x 32]
+constexpr int oA2H = oA1L + kBlk, oA2L = oA2H + 2 * kBlk;         // H1            [128 x 64]
+constexpr int oA3H = oA2L + 2 * kBlk, oA3L = oA3H + 2 * kBlk;     // dZ2 then dZ1  [128 x 64]
+constexpr int oW1H = oA3L + 2 * kBlk, oW1L = oW1H + 8192;         // W1 [64 x 32]
+constexpr int oW2H = oW1L + 8192, oW2L = oW2H + 16384;            // W2 [64 x 64] (two [64 x 32] blocks)
+constexpr int oMisc = oW2L + 16384;
+constexpr size_t kSmem = 1024 + oMisc + 3072;
+constexpr uint32_t cD1 = 0, cD2 = 64, cG2 = 128, cG1 = 192, cW2 = 256, cW1 = 320;
+
+// column-wise sum over the 32 lanes of a warp of v[0..31]; lane j returns the total of column j (recursive halving, 31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+    #pragma unroll
+    for (int n = 16; n >= 1; n >>= 1) {
+        const bool up = (lane & n) != 0;
+        #pragma unroll
+        for (int i = 0; i < n; i++) {
+            const float keep = up ? v[i + n] : v[i], send = up ? v[i] : v[i + n];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return v[0];
+}
+}  // namespace bwdtc
+
+__global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdArgs a) {
+    using namespace bwdtc;
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    float* b1s = reinterpret_cast<float*>(sm + oMisc);          // 64
+    float* b2s = b1s + 64;                                      // 64
+    float* w3s = b2s + 64;                                      // [4][64]
+    LevelSm* lv = reinterpret_cast<LevelSm*>(w3s + 256);        // 16 * 20 B = 320 B  (ends at 1856)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oMisc + 2048);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t *a1_full = bars, *d1_full = bars + 1, *a2_full = bars + 2, *d2_full = bars + 3, *a3_full = bars + 4, *r3_done = bars + 5,
+             *d3_full = bars + 6, *a4_full = bars + 7, *r4_done = bars + 8, *d4_full = bars + 9;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < D_H * D_IN; i += kThreads) {           // W1 [64][32]
+        const int n = i / D_IN, k = i % D_IN; const float v = a.mlp.w1[i], h = tf32_hi(v);
+        *reinterpret_cast<float*>(sm + oW1H + sw_off(n, k)) = h; *reinterpret_cast<float*>(sm + oW1L + sw_off(n, k)) = v - h;
+    }
+    for (int i = tid; i < D_H * D_H; i += kThreads) {            // W2 [64][64]
+        const int n = i / D_H, k = i % D_H; const float v = a.mlp.w2[i], h = tf32_hi(v);
+        const uint32_t o = (k >> 5) * 8192 + sw_off(n, k & 31);
+        *reinterpret_cast<float*>(sm + oW2H + o) = h; *reinterpret_cast<float*>(sm + oW2L + o) = v - h;
+    }
+    for (int i = tid; i < D_OUT * D_H; i += kThreads) w3s[i] = a.mlp.w3[i];
+    for (int i = tid; i < D_H; i += kThreads) { b1s[i] = a.mlp.b1[i]; b2s[i] = a.mlp.b2[i]; }
+    if (tid < 16) {
+        LevelSm L; const int l = tid;
+        if (l < (int)a.hg.n_levels) {
+            L.offset = a.hg.offsets[l]; L.size = a.hg.sizes[l]; L.res = a.hg.ress[l]; L.scale = a.hg.scales[l];
+            L.hashed = (uint64_t)L.res * L.res * L.res > (uint64_t)L.size ? 1u : 0u;
+        } else { L.offset = 0; L.size = 8; L.res = 2; L.scale = 1.f; L.hashed = 0; }
+        lv[l] = L;
+    }
+    if (tid == 0) {
+        tc::mbar_init(a1_full, 256); tc::mbar_init(d1_full, 1); tc::mbar_init(a2_full, 128); tc::mbar_init(d2_full, 1);
+        tc::mbar_init(a3_full, 128); tc::mbar_init(r3_done, 256); tc::mbar_init(d3_full, 1); tc::mbar_init(a4_full, 128);
+        tc::mbar_init(r4_done, 256); tc::mbar_init(d4_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 12) tc::tmem_alloc(tmem_slot, kTmemCols);
+    // the A3 tiles are read MN-major with M = 128, i.e. two 16 KB blocks past each half: keep them finite
+    for (int i = tid; i < (oW1H - oA3H) / 4; i += kThreads) reinterpret_cast<float*>(sm + oA3H)[i] = 0.f;
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t sbase = tc::smem_u32(sm);
+
+    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
+    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
+    const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
+    const float Go = (a.g_loss_orient && a.n_evals >= 7) ? *a.g_loss_orient / (float)m_pad : 0.f;
+    const float Gs = (a.g_loss_smooth && a.n_evals > 7) ? *a.g_loss_smooth / (3.f * (float)m_pad) : 0.f;
+    const bool need_ptaps = Gs != 0.f;
+    const bool need_taps = a.n_evals >= 7 && (need_ptaps || Go != 0.f || lit || a.g_normals != nullptr);
+    const int e_end = !need_taps ? 1 : (need_ptaps ? 13 : 7);
+    const float inv2b = 2.f * a.bound;
+    uint32_t it = 0;
+
+    if (warp < 4) {
+        // ================================ owners ================================
+        const int r = tid;
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        float light[3] = {0.f, 0.f, 0.f};
+        if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
+        // persistent partial sums over this warp's rows: lane j owns columns j and j+32 of dW3[o][.] ; db3 on lane o
+        float aw3[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, ab3 = 0.f;
+        for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+            const uint32_t row = tile * T + r;
+            const bool in_range = row < m_pad, real = row < M;
+            float d[3] = {0.f, 0.f, 0.f};
+            if (real && a.dirs) { d[0] = a.dirs[3 * (size_t)row]; d[1] = a.dirs[3 * (size_t)row + 1]; d[2] = a.dirs[3 * (size_t)row + 2]; }
+            float dh[4] = {0.f, 0.f, 0.f, 0.f}, dtap[12];
+            #pragma unroll
+            for (int i = 0; i < 12; i++) dtap[i] = 0.f;
+            if (in_range) sample_out_grads(a, row, real, d, lit, light, Go, Gs, need_ptaps, dh, dtap);
+            for (int e = 0; e < e_end; e++, it++) {
+                const uint32_t par = it & 1;
+                float dO[4] = {0.f, 0.f, 0.f, 0.f};
+                if (e == 0) { dO[0] = dh[0]; dO[1] = dh[1]; dO[2] = dh[2]; dO[3] = dh[3]; }
+                else {
+                    #pragma unroll
+                    for (int i = 0; i < 12; i++) if (i == e - 1) dO[0] = dtap[i];
+                }
+                uint32_t m1[2] = {0u, 0u};
+                // ---- epilogue 1: H1 = relu(D1 + b1) -> A2 ; remember the ReLU mask ----
+                tc::mbar_wait(d1_full, par);
+                tc::tc_fence_after();
+                #pragma unroll 1
+                for (int c0 = 0; c0 < D_H; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(lane_addr + cD1 + (uint32_t)c0, v);
+                    uint32_t mk = 0u;
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        float h[4], l[4];
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float t = fmaxf(__uint_as_float(v[4 * q + j]) + b1s[c0 + 4 * q + j], 0.f);
+                            if (t > 0.f) mk |= 1u << (4 * q + j);
+                            h[j] = tf32_hi(t); l[j] = t - h[j];
+                        }
+                        const uint32_t o = (c0 >> 5) * kBlk + sw_off(r, 4 * q);
+                        *reinterpret_cast<float4*>(sm + oA2H + o) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(sm + oA2L + o) = make_float4(l[0], l[1], l[2], l[3]);
+                    }
+                    m1[c0 >> 5] = mk;
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                mbar_arrive(a2_full);
+                // ---- epilogue 2: H2 = relu(D2 + b2) ; dZ2 = relu'(H2) * (dO W3) -> A3 ; dW3 / db3 partial sums ----
+                tc::mbar_wait(d2_full, par);
+                tc::tc_fence_after();
+                if (it > 0) { tc::mbar_wait(d4_full, (it - 1) & 1); tc::mbar_wait(r4_done, (it - 1) & 1); }   // A3 free (previous evaluation)
+                #pragma unroll 1
+                for (int c0 = 0; c0 < D_H; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(lane_addr + cD2 + (uint32_t)c0, v);
+                    float h2[32];
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++) h2[j] = fmaxf(__uint_as_float(v[j]) + b2s[c0 + j], 0.f);
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        float h[4], l[4];
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int c = c0 + 4 * q + j;
+                            float g = dO[0] * w3s[c];
+                            if (e == 0) g = fmaf(dO[3], w3s[192 + c], fmaf(dO[2], w3s[128 + c], fmaf(dO[1], w3s[64 + c], g)));
+                            const float t = h2[4 * q + j] > 0.f ? g : 0.f;
+                            h[j] = tf32_hi(t); l[j] = t - h[j];
+                        }
+                        const uint32_t o = (c0 >> 5) * kBlk + sw_off(r, 4 * q);
+                        *reinterpret_cast<float4*>(sm + oA3H + o) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(sm + oA3L + o) = make_float4(l[0], l[1], l[2], l[3]);
+                    }
+                    // dW3[o][c0 + lane] += sum over this warp's rows of dO[o] * H2[.][c0 + lane]
+                    {
+                        float t[32];
+                        #pragma unroll
+                        for (int j = 0; j < 32; j++) t[j] = dO[0] * h2[j];
+                        aw3[0][c0 >> 5] += warp_colsum32(t, lane);
+                        if (e == 0) {
+                            #pragma unroll
+                            for (int o = 1; o < 4; o++) {
+                                #pragma unroll
+                                for (int j = 0; j < 32; j++) t[j] = dO[o] * h2[j];
+                                aw3[o][c0 >> 5] += warp_colsum32(t, lane);
+                            }
+                        }
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                mbar_arrive(a3_full);
+                {   // db3[o] = sum of dO[o] over rows: lane o keeps the total
+                    float s0 = dO[0], s1 = dO[1], s2 = dO[2], s3 = dO[3];
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+                    }
+                    ab3 += lane == 0 ? s0 : (lane == 1 ? s1 : (lane == 2 ? s2 : (lane == 3 ? s3 : 0.f)));
+                }
+                // ---- epilogue 3: dZ1 = relu'(H1) * dH1 -> A3 (after G2 / WG2 retired and the db2 readers are done) ----
+                tc::mbar_wait(d3_full, par);
+                tc::tc_fence_after();
+                tc::mbar_wait(r3_done, par);
+                #pragma unroll 1
+                for (int c0 = 0; c0 < D_H; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(lane_addr + cG2 + (uint32_t)c0, v);
+                    const uint32_t mk = m1[c0 >> 5];
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        float h[4], l[4];
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float t = (mk >> (4 * q + j)) & 1u ? __uint_as_float(v[4 * q + j]) : 0.f;
+                            h[j] = tf32_hi(t); l[j] = t - h[j];
+                        }
+                        const uint32_t o = (c0 >> 5) * kBlk + sw_off(r, 4 * q);
+                        *reinterpret_cast<float4*>(sm + oA3H + o) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(sm + oA3L + o) = make_float4(l[0], l[1], l[2], l[3]);
+                    }
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                mbar_arrive(a4_full);
+            }
+        }
+        // flush dW3 / db3 partials (one RED per lane per warp)
+        #pragma unroll
+        for (int o = 0; o < 4; o++) { atomicAdd(a.g_mlp.w3 + o * D_H + lane, aw3[o][0]); atomicAdd(a.g_mlp.w3 + o * D_H + 32 + lane, aw3[o][1]); }
+        if (lane < 4) atomicAdd(a.g_mlp.b3 + lane, ab3);
+    } else if (warp < 12) {
+        // ================================ encoders / scatterers ================================
+        const int et = tid - 128, r = et & (T - 1), half = et >> 7;
+        const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        // column sums for db2 / db1: this thread sums column cj over rows [rs, rs + 32)
+        const int cj = et & 63, rs = (et >> 6) * 32;
+        float ab2 = 0.f, ab1 = 0.f;
+        for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+            const uint32_t row = tile * T + r;
+            const bool in_range = row < m_pad, real = row < M;
+            float x[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
+            if (real) { x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2]; }
+            if (a.n_evals > 7 && in_range) {
+                float z[3];
+                if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
+                else gauss_pair(a.seed, row, 1u, z);
+                #pragma unroll
+                for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
+            }
+            for (int e = 0; e < e_end; e++, it++) {
+                const uint32_t par = it & 1;
+                float p[3];
+                eval_pos(e, x, xp, a.bound, p);
+                const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
+                float f[16];
+                #pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; continue; }
+                    const LevelSm L = lv[l0 + i];
+                    const CellW cw = hg_cell(u0, u1, u2, L.scale);
+                    const float2* __restrict__ base = reinterpret_cast<const float2*>(a.table) + L.offset;
+                    float2 v[8];
+                    #pragma unroll
+                    for (int corner = 0; corner < 8; corner++) {
+                        const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
+                        v[corner] = __ldg(base + hg_index(cx, cy, cz, L));
+                    }
+                    float f0 = 0.f, f1 = 0.f;
+                    #pragma unroll
+                    for (int corner = 0; corner < 8; corner++) {
+                        const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
+                        const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
+                        const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
+                        const float wt = wx * wy * wz;
+                        f0 = fmaf(wt, v[corner].x, f0); f1 = fmaf(wt, v[corner].y, f1);
+                    }
+                    f[2 * i] = f0; f[2 * i + 1] = f1;
+                }
+                // A1 is free once WG1 of the previous evaluation retired (d4_full), which this thread waited for when it scattered
+                #pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (i >= lcount) continue;
+                    const int k = 2 * (l0 + i);
+                    const float h0 = tf32_hi(f[2 * i]), h1 = tf32_hi(f[2 * i + 1]);
+                    const uint32_t o = sw_off(r, k);
+                    *reinterpret_cast<float2*>(sm + oA1H + o) = make_float2(h0, h1);
+                    *reinterpret_cast<float2*>(sm + oA1L + o) = make_float2(f[2 * i] - h0, f[2 * i + 1] - h1);
+                }
+                tc::fence_proxy_async();
+                mbar_arrive(a1_full);
+                // db2: column sums of dZ2
+                tc::mbar_wait(a3_full, par);
+                {
+                    float sacc = 0.f;
+                    const uint32_t cb = (uint32_t)(cj >> 5) * kBlk;
+                    #pragma unroll 8
+                    for (int rr = 0; rr < 32; rr++) {
+                        const uint32_t o = cb + sw_off(rs + rr, cj & 31);
+                        sacc += *reinterpret_cast<const float*>(sm + oA3H + o) + *reinterpret_cast<const float*>(sm + oA3L + o);
+                    }
+                    ab2 += sacc;
+                }
+                mbar_arrive(r3_done);
+                // db1: column sums of dZ1
+                tc::mbar_wait(a4_full, par);
+                {
+                    float sacc = 0.f;
+                    const uint32_t cb = (uint32_t)(cj >> 5) * kBlk;
+                    #pragma unroll 8
+                    for (int rr = 0; rr < 32; rr++) {
+                        const uint32_t o = cb + sw_off(rs + rr, cj & 31);
+                        sacc += *reinterpret_cast<const float*>(sm + oA3H + o) + *reinterpret_cast<const float*>(sm + oA3L + o);
+                    }
+                    ab1 += sacc;
+                }
+                mbar_arrive(r4_done);
+                // dEnc (this thread's 16 columns of its row) straight from TMEM, then scatter
+                tc::mbar_wait(d4_full, par);
+                tc::tc_fence_after();
+                uint32_t g[16];
+                tmem_ld16(lane_addr + cG1 + (uint32_t)(2 * l0), g);
+                tc::tc_fence_before();
+                if (in_range) {
+                    #pragma unroll 1
+                    for (int i = 0; i < lcount; i++) {
+                        float g0 = 0.f, g1 = 0.f;
+                        #pragma unroll
+                        for (int q = 0; q < 8; q++) if (q == i) { g0 = __uint_as_float(g[2 * q]); g1 = __uint_as_float(g[2 * q + 1]); }
+                        if (g0 == 0.f && g1 == 0.f) continue;
+                        const LevelSm L = lv[l0 + i];
+                        const CellW cw = hg_cell(u0, u1, u2, L.scale);
+                        float2* __restrict__ base = reinterpret_cast<float2*>(a.g_table) + L.offset;
+                        #pragma unroll
+                        for (int corner = 0; corner < 8; corner++) {
+                            const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
+                            const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
+                            const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
+                            const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
+                            const float wt = wx * wy * wz;
+                            atomicAdd(base + hg_index(cx, cy, cz, L), make_float2(wt * g0, wt * g1));
+                        }
+                    }
+                }
+            }
+        }
+        atomicAdd(a.g_mlp.b2 + cj, ab2);
+        atomicAdd(a.g_mlp.b1 + cj, ab1);
+    } else {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const Operand A1k{sbase + oA1H, sbase + oA1L, (uint32_t)kBlk, 0}, A1m{sbase + oA1H, sbase + oA1L, (uint32_t)kBlk, 1};
+            const Operand A2k{sbase + oA2H, sbase + oA2L, (uint32_t)kBlk, 0}, A2m{sbase + oA2H, sbase + oA2L, (uint32_t)kBlk, 1};
+            const Operand A3k{sbase + oA3H, sbase + oA3L, (uint32_t)kBlk, 0}, A3m{sbase + oA3H, sbase + oA3L, (uint32_t)kBlk, 1};
+            const Operand W1k{sbase + oW1H, sbase + oW1L, 8192u, 0}, W1m{sbase + oW1H, sbase + oW1L, 8192u, 1};
+            const Operand W2k{sbase + oW2H, sbase + oW2L, 8192u, 0}, W2m{sbase + oW2H, sbase + oW2L, 8192u, 1};
+            uint32_t accW = 0;
+            for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+                for (int e = 0; e < e_end; e++, it++) {
+                    const uint32_t par = it & 1;
+                    tc::mbar_wait(a1_full, par); tc::tc_fence_after();
+                    issue_3tf32(tmem + cD1, A1k, W1k, 32, idesc_tf32(128, 64, 0, 0), 0);          // F1
+                    tc::umma_commit(d1_full);
+                    tc::mbar_wait(a2_full, par); tc::tc_fence_after();
+                    issue_3tf32(tmem + cD2, A2k, W2k, 64, idesc_tf32(128, 64, 0, 0), 0);          // F2
+                    tc::umma_commit(d2_full);
+                    tc::mbar_wait(a3_full, par); tc::tc_fence_after();
+                    issue_3tf32(tmem + cG2, A3k, W2m, 64, idesc_tf32(128, 64, 0, 1), 0);          // G2 : dH1 = dZ2 W2
+                    issue_3tf32(tmem + cW2, A3m, A2m, 128, idesc_tf32(128, 64, 1, 1), accW);      // WG2: dW2 += dZ2^T H1
+                    tc::umma_commit(d3_full);
+                    tc::mbar_wait(a4_full, par); tc::tc_fence_after();
+                    issue_3tf32(tmem + cG1, A3k, W1m, 64, idesc_tf32(128, 32, 0, 1), 0);          // G1 : dEnc = dZ1 W1
+                    issue_3tf32(tmem + cW1, A3m, A1m, 128, idesc_tf32(128, 32, 1, 1), accW);      // WG1: dW1 += dZ1^T Enc
+                    tc::umma_commit(d4_full);
+                    accW = 1;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    // ---- flush the TMEM-resident weight gradients: rows 0..63 of dW2 [64 x 64] and dW1 [64 x 32] ----
+    if (warp < 2 && it > 0) {
+        const int j = tid;                                      // TMEM lane == output-feature index
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        #pragma unroll 1
+        for (int c0 = 0; c0 < D_H; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(lane_addr + cW2 + (uint32_t)c0, v);
+            #pragma unroll
+            for (int i = 0; i < 16; i++) atomicAdd(a.g_mlp.w2 + j * D_H + c0 + i, __uint_as_float(v[i]));
+        }
+        #pragma unroll 1
+        for (int c0 = 0; c0 < D_IN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(lane_addr + cW1 + (uint32_t)c0, v);
+            #pragma unroll
+            for (int i = 0; i < 16; i++) atomicAdd(a.g_mlp.w1 + j * D_IN + c0 + i, __uint_as_float(v[i]));
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 12) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, kTmemCols); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1086,6 +1503,7 @@ int ensure_attrs() {
         MI3D_CHECK(cudaFuncSetAttribute(k_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false)));
         MI3D_CHECK(cudaFuncSetAttribute(k_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true)));
         MI3D_CHECK(cudaFuncSetAttribute(k_field_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwdtc::kSmem));
+        MI3D_CHECK(cudaFuncSetAttribute(k_field_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdtc::kSmem));
         g_attr_set = true;
     }
     return MI3D_OK;
@@ -1132,6 +1550,8 @@ int mi3d_hashgrid_backward(const float* x, uint32_t E, const float* grad_out, co
 // MI3D_FIELD_TC=0 selects the FFMA forward kernel (kept for A/B measurements); default is the tcgen05 3xTF32 kernel
 static bool use_tc() { static int v = -1; if (v < 0) { const char* e = getenv("MI3D_FIELD_TC"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
 
+static bool use_tc_bwd() { static int v = -1; if (v < 0) { const char* e = getenv("MI3D_FIELD_TC_BWD"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
+
 int mi3d_field_grid_ctas(int backward) { return num_sms() * (backward ? 1 : 2); }
 
 int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
@@ -1174,7 +1594,8 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     a.tape = tape; a.g_sigmas = grad_sigmas; a.g_rgbs = grad_rgbs; a.g_normals = grad_normals;
     a.g_loss_orient = grad_loss_orient; a.g_loss_smooth = grad_loss_smooth;
     a.g_table = grad_table; a.g_mlp = *grad_mlp;
-    k_field_bwd<<<mi3d_field_grid_ctas(1), NT, smem_bytes(true), (cudaStream_t)stream>>>(a);
+    if (use_tc_bwd()) k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
+    else k_field_bwd<<<mi3d_field_grid_ctas(1), NT, smem_bytes(true), (cudaStream_t)stream>>>(a);
     MI3D_RETURN_LAUNCH();
 }
 

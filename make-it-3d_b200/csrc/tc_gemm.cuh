@@ -38,6 +38,7 @@ struct GemmParams {
     int conv_H, conv_W, conv_bw, conv_bh, cin_blocks;
     int a_z1, b_z1;              // batch decomposition of blockIdx.z for A and B maps; b_batched = 0 -> weights shared
     int b_batched;
+    int b_mn;                    // 1: B is given as [K][N] (N contiguous) and used as an MN-major operand (test path)
     // epilogue
     __half* out;                 // fp16 output or nullptr
     float* out_f32;              // fp32 output or nullptr
@@ -137,8 +138,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format F16 (0) @7/@10, K-major A and B, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int b_mn = 0) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major 128B-swizzle descriptor: LBO = byte distance between 64-element MN blocks, SBO = 1024 B (8 K-rows)
+__device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
 template <int BLOCK_N> struct Cfg {
@@ -204,6 +209,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 } else {
                     tma_load_4d(&map_a, &full_bar[stage], sa, kb * BLOCK_K, m0, az0, az1);
                 }
+                if (p.b_mn) {
+                    #pragma unroll
+                    for (int nb = 0; nb < BLOCK_N / 64; nb++) tma_load_4d(&map_b, &full_bar[stage], sb + nb * 8192, n0 + nb * 64, kb * BLOCK_K, 0, 0);
+                } else
                 tma_load_4d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0, bz0, bz1);
                 if (++stage == C::kStages) { stage = 0; phase ^= 1; }
             }
@@ -211,17 +220,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N);
+            const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.b_mn);
             int stage = 0; uint32_t phase = 0;
             for (int kb = 0; kb < p.num_k_blocks; kb++) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(tiles + (size_t)stage * C::kStageBytes);
-                const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + C::kABytes);
+                const uint64_t da = make_sw128_desc(sa), db = p.b_mn ? make_sw128_desc_mn(sa + C::kABytes, 8192u) : make_sw128_desc(sa + C::kABytes);
                 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-                    // advancing K inside the 128B swizzle atom = +32 B on the start address (>>4 => +2)
-                    umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    // advancing K inside the 128B swizzle atom = +32 B on the start address (>>4 => +2);
+                    // MN-major B: K runs over rows, 16 rows = 2048 B (>>4 => +128)
+                    umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(p.b_mn ? 128 * k : 2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
                 if (++stage == C::kStages) { stage = 0; phase ^= 1; }

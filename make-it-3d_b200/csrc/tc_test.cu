@@ -6,23 +6,38 @@
 extern "C" {
 
 // D[M,N] (fp16 or fp32) = alpha * A[M,K] . B[N,K]^T + bias[N] (+ residual)
-int mi3d_gemm_f16(const void* a, const void* b, void* out, int out_is_f32, int M, int N, int K, int block_n, float alpha,
-                  const float* bias, const void* residual, int epi_mode, mi3d_stream_t stream) {
+static int gemm_f16_impl(const void* a, const void* b, void* out, int out_is_f32, int M, int N, int K, int block_n, float alpha,
+                  const float* bias, const void* residual, int epi_mode, int b_mn, mi3d_stream_t stream) {
     if (M % 128 || K % 64) return MI3D_ERR_ARG;
     if (block_n == 0) block_n = tc::pick_block_n(N, M / 128, 148);
     if (block_n == 0 || N % block_n) return MI3D_ERR_ARG;
     CUtensorMap ma, mb;
     int r = tc::make_map_matrix(&ma, (const __half*)a, K, M, K, 128);
     if (r) return r;
-    r = tc::make_map_matrix(&mb, (const __half*)b, K, N, K, block_n);
+    if (b_mn) {   // B given as [K][N]: boxes of [64 k rows][64 n]
+        const uint64_t dims[4] = {(uint64_t)N, (uint64_t)K, 1, 1};
+        const uint64_t str[4] = {2, (uint64_t)N * 2, (uint64_t)N * K * 2, (uint64_t)N * K * 2};
+        const uint32_t box[4] = {64, 64, 1, 1};
+        r = tc::make_map_f16(&mb, b, dims, str, box);
+    } else r = tc::make_map_matrix(&mb, (const __half*)b, K, N, K, block_n);
     if (r) return r;
     tc::GemmParams p = {};
+    p.b_mn = b_mn;
     p.M = M; p.N = N; p.K = K; p.num_k_blocks = K / 64; p.conv = 0; p.a_z1 = 1; p.b_z1 = 1; p.b_batched = 0;
     p.out = out_is_f32 ? nullptr : (__half*)out; p.out_f32 = out_is_f32 ? (float*)out : nullptr;
     p.ldc = epi_mode == tc::EPI_GEGLU ? N / 2 : (epi_mode == tc::EPI_TRANSPOSED ? M : N);
     p.out_z1 = 1; p.out_s_lo = 0; p.out_s_hi = 0; p.bias = bias; p.row_bias = nullptr; p.rows_per_group = 1;
     p.residual = (const __half*)residual; p.ld_res = N; p.epi_mode = epi_mode; p.alpha = alpha; p.m_valid = M;
     return tc::launch(ma, mb, p, block_n, 1, (cudaStream_t)stream);
+}
+
+int mi3d_gemm_f16(const void* a, const void* b, void* out, int out_is_f32, int M, int N, int K, int block_n, float alpha,
+                  const float* bias, const void* residual, int epi_mode, mi3d_stream_t stream) {
+    return gemm_f16_impl(a, b, out, out_is_f32, M, N, K, block_n, alpha, bias, residual, epi_mode, 0, stream);
+}
+// test path: out[M,N] = A[M,K] . Bt[K,N]  (B consumed as an MN-major UMMA operand)
+int mi3d_gemm_f16_bt(const void* a, const void* bt, void* out, int M, int N, int K, int block_n, mi3d_stream_t stream) {
+    return gemm_f16_impl(a, bt, out, 1, M, N, K, block_n, 1.f, nullptr, nullptr, 0, 1, stream);
 }
 
 // 3x3 stride-1 pad-1 convolution, NHWC fp16: x [N,H,W,Cin], w [Cout][3][3][Cin], y [N,H,W,Cout]

@@ -20,6 +20,7 @@ __device__ void stage(const float* __restrict__ X, int R, int C, uint8_t* hi, ui
 __global__ void __launch_bounds__(160, 1) k_tf32_tile_test(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K, int mode) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int swapv = mode >= 3; if (swapv) mode -= 2;
     const int a_mn = mode == 1, b_mn = mode >= 1;
     const int Ra = a_mn ? K : 128, Ca = a_mn ? 128 : K, Rb = b_mn ? K : N, Cb = b_mn ? N : K;
     const uint32_t a_bytes = (uint32_t)Ra * Ca * 4, b_bytes = (uint32_t)Rb * Cb * 4;
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(160, 1) k_tf32_tile_test(const float* __restri
     if (warp == 4 && (tid & 31) == 0) {
         ftc::Operand oa{tc::smem_u32(a_hi), tc::smem_u32(a_lo), (uint32_t)Ra * 128u, a_mn};
         ftc::Operand ob{tc::smem_u32(b_hi), tc::smem_u32(b_lo), (uint32_t)Rb * 128u, b_mn};
+        ftc::g_swap_lbo_sbo = swapv;
         ftc::issue_3tf32(tmem, oa, ob, K, ftc::idesc_tf32(128, N, a_mn, b_mn), 0);
         tc::umma_commit(bar);
     }
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(160, 1) k_tf32_tile_test(const float* __restri
 }  // namespace
 
 extern "C" int mi3d_tf32_tile_test(const float* a, const float* b, float* d, int N, int K, int mode, mi3d_stream_t stream) {
-    if ((N != 16 && N != 32 && N != 64) || K % 32 || K > 128 || mode < 0 || mode > 2) return MI3D_ERR_ARG;
+    if ((N != 16 && N != 32 && N != 64) || K % 32 || K > 128 || mode < 0 || mode > 4) return MI3D_ERR_ARG;
     const size_t smem = 1024 + 2 * (size_t)128 * K * 4 + 2 * (size_t)N * K * 4 + 64;
     MI3D_CHECK(cudaFuncSetAttribute(k_tf32_tile_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tf32_tile_test<<<1, 160, smem, (cudaStream_t)stream>>>(a, b, d, N, K, mode);

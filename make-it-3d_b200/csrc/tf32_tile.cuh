@@ -43,6 +43,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ int g_swap_lbo_sbo = 0;   // experiment switch used by the unit-test kernel only
 // One operand = (hi base, lo base) of its first block + how to walk it.
 struct Operand { uint32_t hi, lo; uint32_t blk_stride; int mn_major; };
 
@@ -53,8 +54,13 @@ __device__ __forceinline__ uint32_t issue_3tf32(uint32_t tmem_d, const Operand& 
         const uint32_t oa = A.mn_major ? (uint32_t)k8 * 1024u : (uint32_t)(k8 >> 2) * A.blk_stride + (uint32_t)(k8 & 3) * 32u;
         const uint32_t ob = B.mn_major ? (uint32_t)k8 * 1024u : (uint32_t)(k8 >> 2) * B.blk_stride + (uint32_t)(k8 & 3) * 32u;
         const uint32_t la = A.mn_major ? A.blk_stride : 16u, lb = B.mn_major ? B.blk_stride : 16u;
-        const uint64_t dah = desc_sw128(A.hi + oa, la), dal = desc_sw128(A.lo + oa, la);
-        const uint64_t dbh = desc_sw128(B.hi + ob, lb), dbl = desc_sw128(B.lo + ob, lb);
+        uint64_t dah = desc_sw128(A.hi + oa, la), dal = desc_sw128(A.lo + oa, la);
+        uint64_t dbh = desc_sw128(B.hi + ob, lb), dbl = desc_sw128(B.lo + ob, lb);
+        if (g_swap_lbo_sbo) {
+            auto sw = [](uint64_t d) { const uint64_t l = (d >> 16) & 0x3FFF, s = (d >> 32) & 0x3FFF; return (d & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | (s << 16) | (l << 32); };
+            if (A.mn_major) { dah = sw(dah); dal = sw(dal); }
+            if (B.mn_major) { dbh = sw(dbh); dbl = sw(dbl); }
+        }
         umma_tf32(tmem_d, dah, dbh, idesc, acc); acc = 1;
         umma_tf32(tmem_d, dal, dbh, idesc, 1);
         umma_tf32(tmem_d, dah, dbl, idesc, 1);
