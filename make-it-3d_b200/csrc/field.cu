@@ -115,6 +115,34 @@ __device__ __forceinline__ void scatter_levels(float* __restrict__ gtable, const
     }
 }
 
+// gather + trilinear blend of levels [l0, l0 + lcount) (lcount <= 8) of point u into f[2i], f[2i+1]
+__device__ __forceinline__ void gather16(const float* __restrict__ table, const LevelSm* __restrict__ lv, int l0, int lcount,
+                                         float u0, float u1, float u2, float (&f)[16]) {
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; continue; }
+        const LevelSm L = lv[l0 + i];
+        const CellW cw = hg_cell(u0, u1, u2, L.scale);
+        const float2* __restrict__ base = reinterpret_cast<const float2*>(table) + L.offset;
+        float2 v[8];
+        #pragma unroll
+        for (int corner = 0; corner < 8; corner++) {
+            const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
+            v[corner] = __ldg(base + hg_index(cx, cy, cz, L));
+        }
+        float f0 = 0.f, f1 = 0.f;
+        #pragma unroll
+        for (int corner = 0; corner < 8; corner++) {
+            const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
+            const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
+            const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
+            const float wt = wx * wy * wz;
+            f0 = fmaf(wt, v[corner].x, f0); f1 = fmaf(wt, v[corner].y, f1);
+        }
+        f[2 * i] = f0; f[2 * i + 1] = f1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // tile GEMMs over shared memory.  A: [K][TP] (k-major), W: [K][N] row-major, Out: [N][TP].
 // thread -> rows lane*4..+3, columns warp*NC..+NC-1 with NC = N/8.
@@ -983,22 +1011,23 @@ __global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
 //   F1: D1 = Enc W1^T          F2: D2 = H1 W2^T                               (recompute, K-major operands)
 //   G2: dH1 = dZ2 W2           WG2: dW2 += dZ2^T H1   (A3/A2/W2 tiles re-read MN-major: no transposed copies)
 //   G1: dEnc = dZ1 W1          WG1: dW1 += dZ1^T Enc
-// all as 3-term tf32 splits.  dW2 / dW1 accumulate in TMEM across the whole persistent CTA (M = 128 with the upper 64 rows
+// all as 3-term bf16 hi/lo splits (kind::f16, ~2^-16 relative; 16-bit operands can be consumed MN-major, tf32 cannot).  dW2 / dW1 accumulate in TMEM across the whole persistent CTA (M = 128 with the upper 64 rows
 // unused) and are flushed once at the end.  dZ3 -> dH2 (K = 4) and dW3 / db3 stay on the owner threads; db2 / db1 are column
 // sums of the dZ tiles taken by the encoder warps, which also read dEnc straight from TMEM and scatter it (RED.v2.f32).
 // TMEM columns: D1 [0,64) D2 [64,128) dH1 [128,192) dEnc [192,224) dW2 [256,320) dW1 [320,352).
 // ---------------------------------------------------------------------------------------------------------
 namespace bwdtc {
-using namespace ::ftc;
+using namespace ::fbf;
 constexpr int kThreads = 416;
-constexpr int kBlk = 128 * 32 * 4;             // one [128 x 32] fp32 block = 16 KB
+constexpr int kTile = 128 * 128;               // one [128 x 64 bf16] tile = 16 KB
 constexpr uint32_t kTmemCols = 512;
-constexpr int oA1H = 0, oA1L = oA1H + kBlk;                       // Enc           [128 x 32]
-constexpr int oA2H = oA1L + kBlk, oA2L = oA2H + 2 * kBlk;         // H1            [128 x 64]
-constexpr int oA3H = oA2L + 2 * kBlk, oA3L = oA3H + 2 * kBlk;     // dZ2 then dZ1  [128 x 64]
-constexpr int oW1H = oA3L + 2 * kBlk, oW1L = oW1H + 8192;         // W1 [64 x 32]
-constexpr int oW2H = oW1L + 8192, oW2L = oW2H + 16384;            // W2 [64 x 64] (two [64 x 32] blocks)
-constexpr int oMisc = oW2L + 16384;
+// all tiles are [rows x 64 bf16]; hi and lo copies
+constexpr int oEH = 0, oEL = oEH + kTile;                          // Enc  [128 x 64] (cols 32..63 stay zero)
+constexpr int oHH = oEL + kTile, oHL = oHH + kTile;                // H1   [128 x 64]
+constexpr int oZH = oHL + kTile, oZL = oZH + kTile;                // dZ2 then dZ1 [128 x 64]
+constexpr int oW1H = oZL + kTile, oW1L = oW1H + 8192;              // W1 [64 x 64] (cols 32..63 zero)
+constexpr int oW2H = oW1L + 8192, oW2L = oW2H + 8192;              // W2 [64 x 64]
+constexpr int oMisc = oW2L + 8192;
 constexpr size_t kSmem = 1024 + oMisc + 3072;
 constexpr uint32_t cD1 = 0, cD2 = 64, cG2 = 128, cG1 = 192, cW2 = 256, cW1 = 320;
 
@@ -1031,14 +1060,15 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
              *d3_full = bars + 6, *a4_full = bars + 7, *r4_done = bars + 8, *d4_full = bars + 9;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < D_H * D_IN; i += kThreads) {           // W1 [64][32]
-        const int n = i / D_IN, k = i % D_IN; const float v = a.mlp.w1[i], h = tf32_hi(v);
-        *reinterpret_cast<float*>(sm + oW1H + sw_off(n, k)) = h; *reinterpret_cast<float*>(sm + oW1L + sw_off(n, k)) = v - h;
+    for (int i = tid; i < (oMisc - oEH) / 16; i += kThreads) reinterpret_cast<uint4*>(sm + oEH)[i] = make_uint4(0, 0, 0, 0);   // zero pads, finite tiles
+    __syncthreads();
+    for (int i = tid; i < D_H * D_IN; i += kThreads) {           // W1 [64][32] -> rows j, cols i (K-major for F1, MN-major for G1)
+        const int n = i / D_IN, k = i % D_IN; __nv_bfloat16 h, l; split_bf16(a.mlp.w1[i], h, l);
+        *reinterpret_cast<__nv_bfloat16*>(sm + oW1H + sw_off16(n, k)) = h; *reinterpret_cast<__nv_bfloat16*>(sm + oW1L + sw_off16(n, k)) = l;
     }
     for (int i = tid; i < D_H * D_H; i += kThreads) {            // W2 [64][64]
-        const int n = i / D_H, k = i % D_H; const float v = a.mlp.w2[i], h = tf32_hi(v);
-        const uint32_t o = (k >> 5) * 8192 + sw_off(n, k & 31);
-        *reinterpret_cast<float*>(sm + oW2H + o) = h; *reinterpret_cast<float*>(sm + oW2L + o) = v - h;
+        const int n = i / D_H, k = i % D_H; __nv_bfloat16 h, l; split_bf16(a.mlp.w2[i], h, l);
+        *reinterpret_cast<__nv_bfloat16*>(sm + oW2H + sw_off16(n, k)) = h; *reinterpret_cast<__nv_bfloat16*>(sm + oW2L + sw_off16(n, k)) = l;
     }
     for (int i = tid; i < D_OUT * D_H; i += kThreads) w3s[i] = a.mlp.w3[i];
     for (int i = tid; i < D_H; i += kThreads) { b1s[i] = a.mlp.b1[i]; b2s[i] = a.mlp.b2[i]; }
@@ -1057,8 +1087,6 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         tc::fence_barrier_init();
     }
     if (warp == 12) tc::tmem_alloc(tmem_slot, kTmemCols);
-    // the A3 tiles are read MN-major with M = 128, i.e. two 16 KB blocks past each half: keep them finite
-    for (int i = tid; i < (oW1H - oA3H) / 4; i += kThreads) reinterpret_cast<float*>(sm + oA3H)[i] = 0.f;
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
@@ -1111,18 +1139,15 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     uint32_t v[32];
                     tc::tmem_ld32(lane_addr + cD1 + (uint32_t)c0, v);
                     uint32_t mk = 0u;
+                    float tv[32];
                     #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        float h[4], l[4];
-                        #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const float t = fmaxf(__uint_as_float(v[4 * q + j]) + b1s[c0 + 4 * q + j], 0.f);
-                            if (t > 0.f) mk |= 1u << (4 * q + j);
-                            h[j] = tf32_hi(t); l[j] = t - h[j];
-                        }
-                        const uint32_t o = (c0 >> 5) * kBlk + sw_off(r, 4 * q);
-                        *reinterpret_cast<float4*>(sm + oA2H + o) = make_float4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<float4*>(sm + oA2L + o) = make_float4(l[0], l[1], l[2], l[3]);
+                    for (int j = 0; j < 32; j++) { const float t = fmaxf(__uint_as_float(v[j]) + b1s[c0 + j], 0.f); if (t > 0.f) mk |= 1u << j; tv[j] = t; }
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint4 hh, ll;
+                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), hh, ll);
+                        const uint32_t o = sw_off16(r, c0 + 8 * q);
+                        *reinterpret_cast<uint4*>(sm + oHH + o) = hh; *reinterpret_cast<uint4*>(sm + oHL + o) = ll;
                     }
                     m1[c0 >> 5] = mk;
                 }
@@ -1140,20 +1165,20 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     float h2[32];
                     #pragma unroll
                     for (int j = 0; j < 32; j++) h2[j] = fmaxf(__uint_as_float(v[j]) + b2s[c0 + j], 0.f);
+                    float tv[32];
                     #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        float h[4], l[4];
-                        #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int c = c0 + 4 * q + j;
-                            float g = dO[0] * w3s[c];
-                            if (e == 0) g = fmaf(dO[3], w3s[192 + c], fmaf(dO[2], w3s[128 + c], fmaf(dO[1], w3s[64 + c], g)));
-                            const float t = h2[4 * q + j] > 0.f ? g : 0.f;
-                            h[j] = tf32_hi(t); l[j] = t - h[j];
-                        }
-                        const uint32_t o = (c0 >> 5) * kBlk + sw_off(r, 4 * q);
-                        *reinterpret_cast<float4*>(sm + oA3H + o) = make_float4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<float4*>(sm + oA3L + o) = make_float4(l[0], l[1], l[2], l[3]);
+                    for (int j = 0; j < 32; j++) {
+                        const int c = c0 + j;
+                        float g = dO[0] * w3s[c];
+                        if (e == 0) g = fmaf(dO[3], w3s[192 + c], fmaf(dO[2], w3s[128 + c], fmaf(dO[1], w3s[64 + c], g)));
+                        tv[j] = h2[j] > 0.f ? g : 0.f;
+                    }
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint4 hh, ll;
+                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), hh, ll);
+                        const uint32_t o = sw_off16(r, c0 + 8 * q);
+                        *reinterpret_cast<uint4*>(sm + oZH + o) = hh; *reinterpret_cast<uint4*>(sm + oZL + o) = ll;
                     }
                     // dW3[o][c0 + lane] += sum over this warp's rows of dO[o] * H2[.][c0 + lane]
                     {
@@ -1192,17 +1217,15 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     uint32_t v[32];
                     tc::tmem_ld32(lane_addr + cG2 + (uint32_t)c0, v);
                     const uint32_t mk = m1[c0 >> 5];
+                    float tv[32];
                     #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        float h[4], l[4];
-                        #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const float t = (mk >> (4 * q + j)) & 1u ? __uint_as_float(v[4 * q + j]) : 0.f;
-                            h[j] = tf32_hi(t); l[j] = t - h[j];
-                        }
-                        const uint32_t o = (c0 >> 5) * kBlk + sw_off(r, 4 * q);
-                        *reinterpret_cast<float4*>(sm + oA3H + o) = make_float4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<float4*>(sm + oA3L + o) = make_float4(l[0], l[1], l[2], l[3]);
+                    for (int j = 0; j < 32; j++) tv[j] = (mk >> j) & 1u ? __uint_as_float(v[j]) : 0.f;
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint4 hh, ll;
+                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), hh, ll);
+                        const uint32_t o = sw_off16(r, c0 + 8 * q);
+                        *reinterpret_cast<uint4*>(sm + oZH + o) = hh; *reinterpret_cast<uint4*>(sm + oZL + o) = ll;
                     }
                 }
                 tc::fence_proxy_async();
@@ -1234,56 +1257,44 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 #pragma unroll
                 for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
             }
+            float f[16], fn[16];
+            {
+                float p[3];
+                eval_pos(0, x, xp, a.bound, p);
+                gather16(a.table, lv, l0, lcount, (p[0] + a.bound) / inv2b, (p[1] + a.bound) / inv2b, (p[2] + a.bound) / inv2b, f);
+            }
             for (int e = 0; e < e_end; e++, it++) {
                 const uint32_t par = it & 1;
                 float p[3];
                 eval_pos(e, x, xp, a.bound, p);
                 const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
-                float f[16];
-                #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; continue; }
-                    const LevelSm L = lv[l0 + i];
-                    const CellW cw = hg_cell(u0, u1, u2, L.scale);
-                    const float2* __restrict__ base = reinterpret_cast<const float2*>(a.table) + L.offset;
-                    float2 v[8];
-                    #pragma unroll
-                    for (int corner = 0; corner < 8; corner++) {
-                        const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
-                        v[corner] = __ldg(base + hg_index(cx, cy, cz, L));
-                    }
-                    float f0 = 0.f, f1 = 0.f;
-                    #pragma unroll
-                    for (int corner = 0; corner < 8; corner++) {
-                        const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
-                        const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
-                        const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
-                        const float wt = wx * wy * wz;
-                        f0 = fmaf(wt, v[corner].x, f0); f1 = fmaf(wt, v[corner].y, f1);
-                    }
-                    f[2 * i] = f0; f[2 * i + 1] = f1;
-                }
                 // A1 is free once WG1 of the previous evaluation retired (d4_full), which this thread waited for when it scattered
                 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     if (i >= lcount) continue;
                     const int k = 2 * (l0 + i);
-                    const float h0 = tf32_hi(f[2 * i]), h1 = tf32_hi(f[2 * i + 1]);
-                    const uint32_t o = sw_off(r, k);
-                    *reinterpret_cast<float2*>(sm + oA1H + o) = make_float2(h0, h1);
-                    *reinterpret_cast<float2*>(sm + oA1L + o) = make_float2(f[2 * i] - h0, f[2 * i + 1] - h1);
+                    __nv_bfloat16 h0, l0b, h1, l1b;
+                    split_bf16(f[2 * i], h0, l0b); split_bf16(f[2 * i + 1], h1, l1b);
+                    const uint32_t o = sw_off16(r, k);
+                    *reinterpret_cast<__nv_bfloat162*>(sm + oEH + o) = __halves2bfloat162(h0, h1);
+                    *reinterpret_cast<__nv_bfloat162*>(sm + oEL + o) = __halves2bfloat162(l0b, l1b);
                 }
                 tc::fence_proxy_async();
                 mbar_arrive(a1_full);
+                // prefetch the next evaluation's gather while the MMA / epilogue chain of this one runs
+                if (e + 1 < e_end) {
+                    float pn[3];
+                    eval_pos(e + 1, x, xp, a.bound, pn);
+                    gather16(a.table, lv, l0, lcount, (pn[0] + a.bound) / inv2b, (pn[1] + a.bound) / inv2b, (pn[2] + a.bound) / inv2b, fn);
+                }
                 // db2: column sums of dZ2
                 tc::mbar_wait(a3_full, par);
                 {
                     float sacc = 0.f;
-                    const uint32_t cb = (uint32_t)(cj >> 5) * kBlk;
                     #pragma unroll 8
                     for (int rr = 0; rr < 32; rr++) {
-                        const uint32_t o = cb + sw_off(rs + rr, cj & 31);
-                        sacc += *reinterpret_cast<const float*>(sm + oA3H + o) + *reinterpret_cast<const float*>(sm + oA3L + o);
+                        const uint32_t o = sw_off16(rs + rr, cj);
+                        sacc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + oZH + o)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + oZL + o));
                     }
                     ab2 += sacc;
                 }
@@ -1292,11 +1303,10 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 tc::mbar_wait(a4_full, par);
                 {
                     float sacc = 0.f;
-                    const uint32_t cb = (uint32_t)(cj >> 5) * kBlk;
                     #pragma unroll 8
                     for (int rr = 0; rr < 32; rr++) {
-                        const uint32_t o = cb + sw_off(rs + rr, cj & 31);
-                        sacc += *reinterpret_cast<const float*>(sm + oA3H + o) + *reinterpret_cast<const float*>(sm + oA3L + o);
+                        const uint32_t o = sw_off16(rs + rr, cj);
+                        sacc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + oZH + o)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + oZL + o));
                     }
                     ab1 += sacc;
                 }
@@ -1328,6 +1338,8 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                         }
                     }
                 }
+                #pragma unroll
+                for (int i = 0; i < 16; i++) f[i] = fn[i];
             }
         }
         atomicAdd(a.g_mlp.b2 + cj, ab2);
@@ -1335,28 +1347,28 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
     } else {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const Operand A1k{sbase + oA1H, sbase + oA1L, (uint32_t)kBlk, 0}, A1m{sbase + oA1H, sbase + oA1L, (uint32_t)kBlk, 1};
-            const Operand A2k{sbase + oA2H, sbase + oA2L, (uint32_t)kBlk, 0}, A2m{sbase + oA2H, sbase + oA2L, (uint32_t)kBlk, 1};
-            const Operand A3k{sbase + oA3H, sbase + oA3L, (uint32_t)kBlk, 0}, A3m{sbase + oA3H, sbase + oA3L, (uint32_t)kBlk, 1};
-            const Operand W1k{sbase + oW1H, sbase + oW1L, 8192u, 0}, W1m{sbase + oW1H, sbase + oW1L, 8192u, 1};
-            const Operand W2k{sbase + oW2H, sbase + oW2L, 8192u, 0}, W2m{sbase + oW2H, sbase + oW2L, 8192u, 1};
+            const Operand Ek{sbase + oEH, sbase + oEL, 16u, 0}, Em{sbase + oEH, sbase + oEL, (uint32_t)kTile, 1};
+            const Operand Hk{sbase + oHH, sbase + oHL, 16u, 0}, Hm{sbase + oHH, sbase + oHL, (uint32_t)kTile, 1};
+            const Operand Zk{sbase + oZH, sbase + oZL, 16u, 0}, Zm{sbase + oZH, sbase + oZL, (uint32_t)kTile, 1};   // M = 128: block 1 = the next tile (finite, rows 64.. unused)
+            const Operand W1k{sbase + oW1H, sbase + oW1L, 16u, 0}, W1m{sbase + oW1H, sbase + oW1L, 8192u, 1};
+            const Operand W2k{sbase + oW2H, sbase + oW2L, 16u, 0}, W2m{sbase + oW2H, sbase + oW2L, 8192u, 1};
             uint32_t accW = 0;
             for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
                 for (int e = 0; e < e_end; e++, it++) {
                     const uint32_t par = it & 1;
                     tc::mbar_wait(a1_full, par); tc::tc_fence_after();
-                    issue_3tf32(tmem + cD1, A1k, W1k, 32, idesc_tf32(128, 64, 0, 0), 0);          // F1
+                    issue_3bf16(tmem + cD1, Ek, W1k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F1 (K = 32 + 32 zero columns)
                     tc::umma_commit(d1_full);
                     tc::mbar_wait(a2_full, par); tc::tc_fence_after();
-                    issue_3tf32(tmem + cD2, A2k, W2k, 64, idesc_tf32(128, 64, 0, 0), 0);          // F2
+                    issue_3bf16(tmem + cD2, Hk, W2k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F2
                     tc::umma_commit(d2_full);
                     tc::mbar_wait(a3_full, par); tc::tc_fence_after();
-                    issue_3tf32(tmem + cG2, A3k, W2m, 64, idesc_tf32(128, 64, 0, 1), 0);          // G2 : dH1 = dZ2 W2
-                    issue_3tf32(tmem + cW2, A3m, A2m, 128, idesc_tf32(128, 64, 1, 1), accW);      // WG2: dW2 += dZ2^T H1
+                    issue_3bf16(tmem + cG2, Zk, W2m, 64, idesc_bf16(128, 64, 0, 1), 0);           // G2 : dH1 = dZ2 W2
+                    issue_3bf16(tmem + cW2, Zm, Hm, 128, idesc_bf16(128, 64, 1, 1), accW);       // WG2: dW2 += dZ2^T H1
                     tc::umma_commit(d3_full);
                     tc::mbar_wait(a4_full, par); tc::tc_fence_after();
-                    issue_3tf32(tmem + cG1, A3k, W1m, 64, idesc_tf32(128, 32, 0, 1), 0);          // G1 : dEnc = dZ1 W1
-                    issue_3tf32(tmem + cW1, A3m, A1m, 128, idesc_tf32(128, 32, 1, 1), accW);      // WG1: dW1 += dZ1^T Enc
+                    issue_3bf16(tmem + cG1, Zk, W1m, 64, idesc_bf16(128, 32, 0, 1), 0);           // G1 : dEnc = dZ1 W1
+                    issue_3bf16(tmem + cW1, Zm, Em, 128, idesc_bf16(128, 32, 1, 1), accW);       // WG1: dW1 += dZ1^T Enc
                     tc::umma_commit(d4_full);
                     accW = 1;
                 }

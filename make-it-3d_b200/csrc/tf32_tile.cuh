@@ -69,3 +69,51 @@ __device__ __forceinline__ uint32_t issue_3tf32(uint32_t tmem_d, const Operand& 
 }
 
 }  // namespace ftc
+
+// ---------------------------------------------------------------------------------------------------------------------
+// bf16 2-way split tiles (kind::f16, bf16 operands): x = hi + lo with hi = bf16(x), lo = bf16(x - hi)  -> ~2^-16 relative,
+// used by the fused field BACKWARD where gradients tolerate it and where 16-bit operands may be consumed MN-major
+// (kind::tf32 has no working MN-major form; the 16-bit one is verified by tools/explore_mn.py / mi3d_gemm_f16_bt).
+// Storage: [rows][64 bf16] = 128-byte rows, 8-row swizzle atoms; the same tile is read K-major (rows = M/N, +32 B per
+// K = 16 step) or MN-major (rows = K, +2048 B per K = 16 step, LBO = distance to the next 64-column block).
+// ---------------------------------------------------------------------------------------------------------------------
+#include <cuda_bf16.h>
+namespace fbf {
+using ftc::mbar_arrive;
+using ftc::tmem_ld16;
+
+// byte offset of element (row, c) inside a [rows x 64 bf16] tile
+__device__ __forceinline__ uint32_t sw_off16(int row, int c) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((c >> 3) ^ (row & 7)) & 7) << 4) + ((c & 7) << 1));
+}
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// pack 8 floats into one 16-byte chunk of hi parts and one of lo parts
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    __align__(16) __nv_bfloat16 h[8], l[8];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) split_bf16(x[i], h[i], l[i]);
+    hi = *reinterpret_cast<const uint4*>(h); lo = *reinterpret_cast<const uint4*>(l);
+}
+// kind::f16 instruction descriptor with BF16 operands (format 1), fp32 accumulate
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+struct Operand { uint32_t hi, lo; uint32_t lbo; int mn_major; };    // one 64-column block (or M = 128 MN-major: lbo = next block)
+
+// D[128 x N] (+)= A . B over K elements (K % 16 == 0, K-major operands: K <= 64), 3 MMAs per K = 16 step
+__device__ __forceinline__ uint32_t issue_3bf16(uint32_t tmem_d, const Operand& A, const Operand& B, int K, uint32_t idesc, uint32_t acc) {
+    for (int k16 = 0; k16 < K / 16; k16++) {
+        const uint32_t oa = A.mn_major ? (uint32_t)k16 * 2048u : (uint32_t)k16 * 32u;
+        const uint32_t ob = B.mn_major ? (uint32_t)k16 * 2048u : (uint32_t)k16 * 32u;
+        const uint64_t dah = ftc::desc_sw128(A.hi + oa, A.mn_major ? A.lbo : 16u), dal = ftc::desc_sw128(A.lo + oa, A.mn_major ? A.lbo : 16u);
+        const uint64_t dbh = ftc::desc_sw128(B.hi + ob, B.mn_major ? B.lbo : 16u), dbl = ftc::desc_sw128(B.lo + ob, B.mn_major ? B.lbo : 16u);
+        tc::umma_f16(tmem_d, dah, dbh, idesc, acc); acc = 1;
+        tc::umma_f16(tmem_d, dal, dbh, idesc, 1);
+        tc::umma_f16(tmem_d, dah, dbl, idesc, 1);
+    }
+    return acc;
+}
+}  // namespace fbf
