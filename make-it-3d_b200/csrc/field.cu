@@ -115,6 +115,39 @@ __device__ __forceinline__ void scatter_levels(float* __restrict__ gtable, const
     }
 }
 
+// Warp-aggregated variant for the tensor-core backward: lanes are consecutive samples of (mostly) one ray, so at the coarse
+// levels whole runs of lanes fall into the same cell.  A segmented inclusive scan keyed by the table index (5 shuffle steps)
+// folds each run; only the last lane of a run issues the RED.  LSU atomics, not issue slots, bound the backward (ncu: issue 14 %).
+// Must be called by all 32 lanes (inactive lanes pass active = false).
+__device__ __forceinline__ void scatter_level_agg(float* __restrict__ gtable, const LevelSm& L, float u0, float u1, float u2,
+                                                  float g0, float g1, bool active, bool aggregate, int lane) {
+    const CellW cw = hg_cell(u0, u1, u2, L.scale);
+    float2* __restrict__ base = reinterpret_cast<float2*>(gtable) + L.offset;
+    #pragma unroll
+    for (int corner = 0; corner < 8; corner++) {
+        const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
+        const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
+        const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
+        const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
+        const float wt = wx * wy * wz;
+        uint32_t key = active ? hg_index(cx, cy, cz, L) : (0xFFFFFF00u + (uint32_t)lane);
+        float v0 = active ? wt * g0 : 0.f, v1 = active ? wt * g1 : 0.f;
+        if (aggregate) {
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t ku = __shfl_up_sync(0xffffffffu, key, d);
+                const float a0 = __shfl_up_sync(0xffffffffu, v0, d), a1 = __shfl_up_sync(0xffffffffu, v1, d);
+                if (lane >= d && ku == key) { v0 += a0; v1 += a1; }
+            }
+            const uint32_t kn = __shfl_down_sync(0xffffffffu, key, 1);
+            const bool tail = lane == 31 || kn != key;
+            if (active && tail && (v0 != 0.f || v1 != 0.f)) atomicAdd(base + key, make_float2(v0, v1));
+        } else if (active && (v0 != 0.f || v1 != 0.f)) {
+            atomicAdd(base + key, make_float2(v0, v1));
+        }
+    }
+}
+
 // gather + trilinear blend of levels [l0, l0 + lcount) (lcount <= 8) of point u into f[2i], f[2i+1]
 __device__ __forceinline__ void gather16(const float* __restrict__ table, const LevelSm* __restrict__ lv, int l0, int lcount,
                                          float u0, float u1, float u2, float (&f)[16]) {
@@ -1011,7 +1044,8 @@ __global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
 //   F1: D1 = Enc W1^T          F2: D2 = H1 W2^T                               (recompute, K-major operands)
 //   G2: dH1 = dZ2 W2           WG2: dW2 += dZ2^T H1   (A3/A2/W2 tiles re-read MN-major: no transposed copies)
 //   G1: dEnc = dZ1 W1          WG1: dW1 += dZ1^T Enc
-// all as 3-term bf16 hi/lo splits (kind::f16, ~2^-16 relative; 16-bit operands can be consumed MN-major, tf32 cannot).  dW2 / dW1 accumulate in TMEM across the whole persistent CTA (M = 128 with the upper 64 rows
+// all as bf16 3-way splits x = h + m + l with six product terms (kind::f16, fp32-class; 16-bit operands can be consumed
+// MN-major, kind::tf32 cannot).  dW2 / dW1 accumulate in TMEM across the whole persistent CTA (M = 128 with the upper 64 rows
 // unused) and are flushed once at the end.  dZ3 -> dH2 (K = 4) and dW3 / db3 stay on the owner threads; db2 / db1 are column
 // sums of the dZ tiles taken by the encoder warps, which also read dEnc straight from TMEM and scatter it (RED.v2.f32).
 // TMEM columns: D1 [0,64) D2 [64,128) dH1 [128,192) dEnc [192,224) dW2 [256,320) dW1 [320,352).
@@ -1021,13 +1055,13 @@ using namespace ::fbf;
 constexpr int kThreads = 416;
 constexpr int kTile = 128 * 128;               // one [128 x 64 bf16] tile = 16 KB
 constexpr uint32_t kTmemCols = 512;
-// all tiles are [rows x 64 bf16]; hi and lo copies
-constexpr int oEH = 0, oEL = oEH + kTile;                          // Enc  [128 x 64] (cols 32..63 stay zero)
-constexpr int oHH = oEL + kTile, oHL = oHH + kTile;                // H1   [128 x 64]
-constexpr int oZH = oHL + kTile, oZL = oZH + kTile;                // dZ2 then dZ1 [128 x 64]
-constexpr int oW1H = oZL + kTile, oW1L = oW1H + 8192;              // W1 [64 x 64] (cols 32..63 zero)
-constexpr int oW2H = oW1L + 8192, oW2L = oW2H + 8192;              // W2 [64 x 64]
-constexpr int oMisc = oW2L + 8192;
+// every operand = three part tiles (h, m, l) back to back; tiles are [rows x 64 bf16]
+constexpr int oE = 0;                                              // Enc  3 x [128 x 64] (cols 32..63 stay zero)
+constexpr int oH = oE + 3 * kTile;                                 // H1   3 x [128 x 64]
+constexpr int oZ = oH + 3 * kTile;                                 // dZ2 then dZ1, 3 x [128 x 64]
+constexpr int oW1 = oZ + 3 * kTile;                                // W1   3 x [64 x 64] (cols 32..63 zero)
+constexpr int oW2 = oW1 + 3 * 8192;                                // W2   3 x [64 x 64]
+constexpr int oMisc = oW2 + 3 * 8192;
 constexpr size_t kSmem = 1024 + oMisc + 3072;
 constexpr uint32_t cD1 = 0, cD2 = 64, cG2 = 128, cG1 = 192, cW2 = 256, cW1 = 320;
 
@@ -1060,15 +1094,17 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
              *d3_full = bars + 6, *a4_full = bars + 7, *r4_done = bars + 8, *d4_full = bars + 9;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < (oMisc - oEH) / 16; i += kThreads) reinterpret_cast<uint4*>(sm + oEH)[i] = make_uint4(0, 0, 0, 0);   // zero pads, finite tiles
+    for (int i = tid; i < (oMisc - oE) / 16; i += kThreads) reinterpret_cast<uint4*>(sm + oE)[i] = make_uint4(0, 0, 0, 0);   // zero pads, finite tiles
     __syncthreads();
     for (int i = tid; i < D_H * D_IN; i += kThreads) {           // W1 [64][32] -> rows j, cols i (K-major for F1, MN-major for G1)
-        const int n = i / D_IN, k = i % D_IN; __nv_bfloat16 h, l; split_bf16(a.mlp.w1[i], h, l);
-        *reinterpret_cast<__nv_bfloat16*>(sm + oW1H + sw_off16(n, k)) = h; *reinterpret_cast<__nv_bfloat16*>(sm + oW1L + sw_off16(n, k)) = l;
+        const int n = i / D_IN, k = i % D_IN; __nv_bfloat16 h, m, l; split3(a.mlp.w1[i], h, m, l);
+        const uint32_t o = oW1 + sw_off16(n, k);
+        *reinterpret_cast<__nv_bfloat16*>(sm + o) = h; *reinterpret_cast<__nv_bfloat16*>(sm + o + 8192) = m; *reinterpret_cast<__nv_bfloat16*>(sm + o + 16384) = l;
     }
     for (int i = tid; i < D_H * D_H; i += kThreads) {            // W2 [64][64]
-        const int n = i / D_H, k = i % D_H; __nv_bfloat16 h, l; split_bf16(a.mlp.w2[i], h, l);
-        *reinterpret_cast<__nv_bfloat16*>(sm + oW2H + sw_off16(n, k)) = h; *reinterpret_cast<__nv_bfloat16*>(sm + oW2L + sw_off16(n, k)) = l;
+        const int n = i / D_H, k = i % D_H; __nv_bfloat16 h, m, l; split3(a.mlp.w2[i], h, m, l);
+        const uint32_t o = oW2 + sw_off16(n, k);
+        *reinterpret_cast<__nv_bfloat16*>(sm + o) = h; *reinterpret_cast<__nv_bfloat16*>(sm + o + 8192) = m; *reinterpret_cast<__nv_bfloat16*>(sm + o + 16384) = l;
     }
     for (int i = tid; i < D_OUT * D_H; i += kThreads) w3s[i] = a.mlp.w3[i];
     for (int i = tid; i < D_H; i += kThreads) { b1s[i] = a.mlp.b1[i]; b2s[i] = a.mlp.b2[i]; }
@@ -1144,10 +1180,10 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     for (int j = 0; j < 32; j++) { const float t = fmaxf(__uint_as_float(v[j]) + b1s[c0 + j], 0.f); if (t > 0.f) mk |= 1u << j; tv[j] = t; }
                     #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        uint4 hh, ll;
-                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), hh, ll);
-                        const uint32_t o = sw_off16(r, c0 + 8 * q);
-                        *reinterpret_cast<uint4*>(sm + oHH + o) = hh; *reinterpret_cast<uint4*>(sm + oHL + o) = ll;
+                        uint4 ph, pm, pl;
+                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), ph, pm, pl);
+                        const uint32_t o = oH + sw_off16(r, c0 + 8 * q);
+                        *reinterpret_cast<uint4*>(sm + o) = ph; *reinterpret_cast<uint4*>(sm + o + kTile) = pm; *reinterpret_cast<uint4*>(sm + o + 2 * kTile) = pl;
                     }
                     m1[c0 >> 5] = mk;
                 }
@@ -1175,10 +1211,10 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     }
                     #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        uint4 hh, ll;
-                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), hh, ll);
-                        const uint32_t o = sw_off16(r, c0 + 8 * q);
-                        *reinterpret_cast<uint4*>(sm + oZH + o) = hh; *reinterpret_cast<uint4*>(sm + oZL + o) = ll;
+                        uint4 ph, pm, pl;
+                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), ph, pm, pl);
+                        const uint32_t o = oZ + sw_off16(r, c0 + 8 * q);
+                        *reinterpret_cast<uint4*>(sm + o) = ph; *reinterpret_cast<uint4*>(sm + o + kTile) = pm; *reinterpret_cast<uint4*>(sm + o + 2 * kTile) = pl;
                     }
                     // dW3[o][c0 + lane] += sum over this warp's rows of dO[o] * H2[.][c0 + lane]
                     {
@@ -1222,10 +1258,10 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     for (int j = 0; j < 32; j++) tv[j] = (mk >> j) & 1u ? __uint_as_float(v[j]) : 0.f;
                     #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        uint4 hh, ll;
-                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), hh, ll);
-                        const uint32_t o = sw_off16(r, c0 + 8 * q);
-                        *reinterpret_cast<uint4*>(sm + oZH + o) = hh; *reinterpret_cast<uint4*>(sm + oZL + o) = ll;
+                        uint4 ph, pm, pl;
+                        split8(reinterpret_cast<const float(&)[8]>(tv[8 * q]), ph, pm, pl);
+                        const uint32_t o = oZ + sw_off16(r, c0 + 8 * q);
+                        *reinterpret_cast<uint4*>(sm + o) = ph; *reinterpret_cast<uint4*>(sm + o + kTile) = pm; *reinterpret_cast<uint4*>(sm + o + 2 * kTile) = pl;
                     }
                 }
                 tc::fence_proxy_async();
@@ -1273,11 +1309,12 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 for (int i = 0; i < 8; i++) {
                     if (i >= lcount) continue;
                     const int k = 2 * (l0 + i);
-                    __nv_bfloat16 h0, l0b, h1, l1b;
-                    split_bf16(f[2 * i], h0, l0b); split_bf16(f[2 * i + 1], h1, l1b);
-                    const uint32_t o = sw_off16(r, k);
-                    *reinterpret_cast<__nv_bfloat162*>(sm + oEH + o) = __halves2bfloat162(h0, h1);
-                    *reinterpret_cast<__nv_bfloat162*>(sm + oEL + o) = __halves2bfloat162(l0b, l1b);
+                    __nv_bfloat16 h0, m0, q0, h1, m1b, q1;
+                    split3(f[2 * i], h0, m0, q0); split3(f[2 * i + 1], h1, m1b, q1);
+                    const uint32_t o = oE + sw_off16(r, k);
+                    *reinterpret_cast<__nv_bfloat162*>(sm + o) = __halves2bfloat162(h0, h1);
+                    *reinterpret_cast<__nv_bfloat162*>(sm + o + kTile) = __halves2bfloat162(m0, m1b);
+                    *reinterpret_cast<__nv_bfloat162*>(sm + o + 2 * kTile) = __halves2bfloat162(q0, q1);
                 }
                 tc::fence_proxy_async();
                 mbar_arrive(a1_full);
@@ -1293,8 +1330,9 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     float sacc = 0.f;
                     #pragma unroll 8
                     for (int rr = 0; rr < 32; rr++) {
-                        const uint32_t o = sw_off16(rs + rr, cj);
-                        sacc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + oZH + o)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + oZL + o));
+                        const uint32_t o = oZ + sw_off16(rs + rr, cj);
+                        sacc += (__bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o + kTile)))
+                              + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o + 2 * kTile));
                     }
                     ab2 += sacc;
                 }
@@ -1305,8 +1343,9 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     float sacc = 0.f;
                     #pragma unroll 8
                     for (int rr = 0; rr < 32; rr++) {
-                        const uint32_t o = sw_off16(rs + rr, cj);
-                        sacc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + oZH + o)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + oZL + o));
+                        const uint32_t o = oZ + sw_off16(rs + rr, cj);
+                        sacc += (__bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o + kTile)))
+                              + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o + 2 * kTile));
                     }
                     ab1 += sacc;
                 }
@@ -1317,26 +1356,14 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 uint32_t g[16];
                 tmem_ld16(lane_addr + cG1 + (uint32_t)(2 * l0), g);
                 tc::tc_fence_before();
-                if (in_range) {
-                    #pragma unroll 1
-                    for (int i = 0; i < lcount; i++) {
-                        float g0 = 0.f, g1 = 0.f;
-                        #pragma unroll
-                        for (int q = 0; q < 8; q++) if (q == i) { g0 = __uint_as_float(g[2 * q]); g1 = __uint_as_float(g[2 * q + 1]); }
-                        if (g0 == 0.f && g1 == 0.f) continue;
-                        const LevelSm L = lv[l0 + i];
-                        const CellW cw = hg_cell(u0, u1, u2, L.scale);
-                        float2* __restrict__ base = reinterpret_cast<float2*>(a.g_table) + L.offset;
-                        #pragma unroll
-                        for (int corner = 0; corner < 8; corner++) {
-                            const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
-                            const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
-                            const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
-                            const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
-                            const float wt = wx * wy * wz;
-                            atomicAdd(base + hg_index(cx, cy, cz, L), make_float2(wt * g0, wt * g1));
-                        }
-                    }
+                #pragma unroll 1
+                for (int i = 0; i < lcount; i++) {
+                    float g0 = 0.f, g1 = 0.f;
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) if (q == i) { g0 = __uint_as_float(g[2 * q]); g1 = __uint_as_float(g[2 * q + 1]); }
+                    const LevelSm L = lv[l0 + i];
+                    // aggregate where a cell spans several march steps (2 / scale  >  ~1.5 dt_min): levels 0..7 of the reference grid
+                    scatter_level_agg(a.g_table, L, u0, u1, u2, g0, g1, in_range, L.scale < 200.f, lane);
                 }
                 #pragma unroll
                 for (int i = 0; i < 16; i++) f[i] = fn[i];
@@ -1347,28 +1374,29 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
     } else {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const Operand Ek{sbase + oEH, sbase + oEL, 16u, 0}, Em{sbase + oEH, sbase + oEL, (uint32_t)kTile, 1};
-            const Operand Hk{sbase + oHH, sbase + oHL, 16u, 0}, Hm{sbase + oHH, sbase + oHL, (uint32_t)kTile, 1};
-            const Operand Zk{sbase + oZH, sbase + oZL, 16u, 0}, Zm{sbase + oZH, sbase + oZL, (uint32_t)kTile, 1};   // M = 128: block 1 = the next tile (finite, rows 64.. unused)
-            const Operand W1k{sbase + oW1H, sbase + oW1L, 16u, 0}, W1m{sbase + oW1H, sbase + oW1L, 8192u, 1};
-            const Operand W2k{sbase + oW2H, sbase + oW2L, 16u, 0}, W2m{sbase + oW2H, sbase + oW2L, 8192u, 1};
+            // MN-major with M = 128 reads a second 64-column block at +lbo: it lands on the next part tile (finite; rows 64.. of D unused)
+            const Operand Ek{sbase + oE, (uint32_t)kTile, 16u, 0}, Em{sbase + oE, (uint32_t)kTile, (uint32_t)kTile, 1};
+            const Operand Hk{sbase + oH, (uint32_t)kTile, 16u, 0}, Hm{sbase + oH, (uint32_t)kTile, (uint32_t)kTile, 1};
+            const Operand Zk{sbase + oZ, (uint32_t)kTile, 16u, 0}, Zm{sbase + oZ, (uint32_t)kTile, (uint32_t)kTile, 1};
+            const Operand W1k{sbase + oW1, 8192u, 16u, 0}, W1m{sbase + oW1, 8192u, 8192u, 1};
+            const Operand W2k{sbase + oW2, 8192u, 16u, 0}, W2m{sbase + oW2, 8192u, 8192u, 1};
             uint32_t accW = 0;
             for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
                 for (int e = 0; e < e_end; e++, it++) {
                     const uint32_t par = it & 1;
                     tc::mbar_wait(a1_full, par); tc::tc_fence_after();
-                    issue_3bf16(tmem + cD1, Ek, W1k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F1 (K = 32 + 32 zero columns)
+                    issue_bf16x3(tmem + cD1, Ek, W1k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F1 (K = 32 + 32 zero columns)
                     tc::umma_commit(d1_full);
                     tc::mbar_wait(a2_full, par); tc::tc_fence_after();
-                    issue_3bf16(tmem + cD2, Hk, W2k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F2
+                    issue_bf16x3(tmem + cD2, Hk, W2k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F2
                     tc::umma_commit(d2_full);
                     tc::mbar_wait(a3_full, par); tc::tc_fence_after();
-                    issue_3bf16(tmem + cG2, Zk, W2m, 64, idesc_bf16(128, 64, 0, 1), 0);           // G2 : dH1 = dZ2 W2
-                    issue_3bf16(tmem + cW2, Zm, Hm, 128, idesc_bf16(128, 64, 1, 1), accW);       // WG2: dW2 += dZ2^T H1
+                    issue_bf16x3(tmem + cG2, Zk, W2m, 64, idesc_bf16(128, 64, 0, 1), 0);           // G2 : dH1 = dZ2 W2
+                    issue_bf16x3(tmem + cW2, Zm, Hm, 128, idesc_bf16(128, 64, 1, 1), accW);       // WG2: dW2 += dZ2^T H1
                     tc::umma_commit(d3_full);
                     tc::mbar_wait(a4_full, par); tc::tc_fence_after();
-                    issue_3bf16(tmem + cG1, Zk, W1m, 64, idesc_bf16(128, 32, 0, 1), 0);           // G1 : dEnc = dZ1 W1
-                    issue_3bf16(tmem + cW1, Zm, Em, 128, idesc_bf16(128, 32, 1, 1), accW);       // WG1: dW1 += dZ1^T Enc
+                    issue_bf16x3(tmem + cG1, Zk, W1m, 64, idesc_bf16(128, 32, 0, 1), 0);           // G1 : dEnc = dZ1 W1
+                    issue_bf16x3(tmem + cW1, Zm, Em, 128, idesc_bf16(128, 32, 1, 1), accW);       // WG1: dW1 += dZ1^T Enc
                     tc::umma_commit(d4_full);
                     accW = 1;
                 }

@@ -71,8 +71,8 @@ __device__ __forceinline__ uint32_t issue_3tf32(uint32_t tmem_d, const Operand& 
 }  // namespace ftc
 
 // ---------------------------------------------------------------------------------------------------------------------
-// bf16 2-way split tiles (kind::f16, bf16 operands): x = hi + lo with hi = bf16(x), lo = bf16(x - hi)  -> ~2^-16 relative,
-// used by the fused field BACKWARD where gradients tolerate it and where 16-bit operands may be consumed MN-major
+// bf16 3-way split tiles (kind::f16, bf16 operands): x = h + m + l (each bf16, together ~24 bits) -> fp32-class products,
+// used by the fused field BACKWARD because 16-bit operands may be consumed MN-major
 // (kind::tf32 has no working MN-major form; the 16-bit one is verified by tools/explore_mn.py / mi3d_gemm_f16_bt).
 // Storage: [rows][64 bf16] = 128-byte rows, 8-row swizzle atoms; the same tile is read K-major (rows = M/N, +32 B per
 // K = 16 step) or MN-major (rows = K, +2048 B per K = 16 step, LBO = distance to the next 64-column block).
@@ -86,33 +86,43 @@ using ftc::tmem_ld16;
 __device__ __forceinline__ uint32_t sw_off16(int row, int c) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((c >> 3) ^ (row & 7)) & 7) << 4) + ((c & 7) << 1));
 }
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// 3-way split: x = h + m + l exactly to ~24 bits (fp32-class), each part bf16
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+    h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    m = __float2bfloat16_rn(r1);
+    l = __float2bfloat16_rn(r1 - __bfloat162float(m));
 }
-// pack 8 floats into one 16-byte chunk of hi parts and one of lo parts
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-    __align__(16) __nv_bfloat16 h[8], l[8];
+// pack 8 floats into one 16-byte chunk per part
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& ph, uint4& pm, uint4& pl) {
+    __align__(16) __nv_bfloat16 h[8], m[8], l[8];
     #pragma unroll
-    for (int i = 0; i < 8; i++) split_bf16(x[i], h[i], l[i]);
-    hi = *reinterpret_cast<const uint4*>(h); lo = *reinterpret_cast<const uint4*>(l);
+    for (int i = 0; i < 8; i++) split3(x[i], h[i], m[i], l[i]);
+    ph = *reinterpret_cast<const uint4*>(h); pm = *reinterpret_cast<const uint4*>(m); pl = *reinterpret_cast<const uint4*>(l);
 }
 // kind::f16 instruction descriptor with BF16 operands (format 1), fp32 accumulate
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-struct Operand { uint32_t hi, lo; uint32_t lbo; int mn_major; };    // one 64-column block (or M = 128 MN-major: lbo = next block)
+// one operand: three part tiles laid out back to back (h, m, l at +0, +part_stride, +2 part_stride)
+struct Operand { uint32_t base; uint32_t part_stride; uint32_t lbo; int mn_major; };
 
-// D[128 x N] (+)= A . B over K elements (K % 16 == 0, K-major operands: K <= 64), 3 MMAs per K = 16 step
-__device__ __forceinline__ uint32_t issue_3bf16(uint32_t tmem_d, const Operand& A, const Operand& B, int K, uint32_t idesc, uint32_t acc) {
+// D[128 x N] (+)= A . B over K elements (K % 16 == 0; K-major operands: K <= 64).  Six MMAs per K = 16 step keep every
+// product term down to 2^-16 of the leading one: hh, hm, mh, hl, lh, mm  -> fp32-class accuracy.
+__device__ __forceinline__ uint32_t issue_bf16x3(uint32_t tmem_d, const Operand& A, const Operand& B, int K, uint32_t idesc, uint32_t acc) {
     for (int k16 = 0; k16 < K / 16; k16++) {
         const uint32_t oa = A.mn_major ? (uint32_t)k16 * 2048u : (uint32_t)k16 * 32u;
         const uint32_t ob = B.mn_major ? (uint32_t)k16 * 2048u : (uint32_t)k16 * 32u;
-        const uint64_t dah = ftc::desc_sw128(A.hi + oa, A.mn_major ? A.lbo : 16u), dal = ftc::desc_sw128(A.lo + oa, A.mn_major ? A.lbo : 16u);
-        const uint64_t dbh = ftc::desc_sw128(B.hi + ob, B.mn_major ? B.lbo : 16u), dbl = ftc::desc_sw128(B.lo + ob, B.mn_major ? B.lbo : 16u);
-        tc::umma_f16(tmem_d, dah, dbh, idesc, acc); acc = 1;
-        tc::umma_f16(tmem_d, dal, dbh, idesc, 1);
-        tc::umma_f16(tmem_d, dah, dbl, idesc, 1);
+        const uint32_t la = A.mn_major ? A.lbo : 16u, lb = B.mn_major ? B.lbo : 16u;
+        uint64_t da[3], db[3];
+        #pragma unroll
+        for (int q = 0; q < 3; q++) { da[q] = ftc::desc_sw128(A.base + q * A.part_stride + oa, la); db[q] = ftc::desc_sw128(B.base + q * B.part_stride + ob, lb); }
+        tc::umma_f16(tmem_d, da[0], db[0], idesc, acc); acc = 1;
+        tc::umma_f16(tmem_d, da[0], db[1], idesc, 1);
+        tc::umma_f16(tmem_d, da[1], db[0], idesc, 1);
+        tc::umma_f16(tmem_d, da[0], db[2], idesc, 1);
+        tc::umma_f16(tmem_d, da[2], db[0], idesc, 1);
+        tc::umma_f16(tmem_d, da[1], db[1], idesc, 1);
     }
     return acc;
 }
