@@ -133,14 +133,17 @@ __device__ __forceinline__ void scatter_level_agg(float* __restrict__ gtable, co
         uint32_t key = active ? hg_index(cx, cy, cz, L) : (0xFFFFFF00u + (uint32_t)lane);
         float v0 = active ? wt * g0 : 0.f, v1 = active ? wt * g1 : 0.f;
         if (aggregate) {
+            // runs = maximal stretches of ADJACENT lanes with the same key (equal keys further apart stay separate runs)
+            const uint32_t kp = __shfl_up_sync(0xffffffffu, key, 1);
+            const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || kp != key);
+            const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
             #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t ku = __shfl_up_sync(0xffffffffu, key, d);
+                const int su = __shfl_up_sync(0xffffffffu, seg, d);
                 const float a0 = __shfl_up_sync(0xffffffffu, v0, d), a1 = __shfl_up_sync(0xffffffffu, v1, d);
-                if (lane >= d && ku == key) { v0 += a0; v1 += a1; }
+                if (lane >= d && su == seg) { v0 += a0; v1 += a1; }
             }
-            const uint32_t kn = __shfl_down_sync(0xffffffffu, key, 1);
-            const bool tail = lane == 31 || kn != key;
+            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
             if (active && tail && (v0 != 0.f || v1 != 0.f)) atomicAdd(base + key, make_float2(v0, v1));
         } else if (active && (v0 != 0.f || v1 != 0.f)) {
             atomicAdd(base + key, make_float2(v0, v1));
