@@ -151,31 +151,35 @@ __device__ __forceinline__ void scatter_level_agg(float* __restrict__ gtable, co
     }
 }
 
-// gather + trilinear blend of levels [l0, l0 + lcount) (lcount <= 8) of point u into f[2i], f[2i+1]
+// gather + trilinear blend of levels [l0, l0 + lcount) (lcount <= 8) of point u into f[2i], f[2i+1].
+// Levels are processed in PAIRS: 16 independent 8-byte loads are in flight per thread before any is consumed (the kernels
+// are bound by gather latency, not by issue slots or L1 wavefronts -- ncu: long_scoreboard dominates).
 __device__ __forceinline__ void gather16(const float* __restrict__ table, const LevelSm* __restrict__ lv, int l0, int lcount,
                                          float u0, float u1, float u2, float (&f)[16]) {
     #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; continue; }
-        const LevelSm L = lv[l0 + i];
-        const CellW cw = hg_cell(u0, u1, u2, L.scale);
-        const float2* __restrict__ base = reinterpret_cast<const float2*>(table) + L.offset;
-        float2 v[8];
+    for (int i = 0; i < 8; i += 2) {
+        if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; f[2 * i + 2] = 0.f; f[2 * i + 3] = 0.f; continue; }
+        const bool two = i + 1 < lcount;
+        const LevelSm La = lv[l0 + i], Lb = lv[l0 + (two ? i + 1 : i)];
+        const CellW ca = hg_cell(u0, u1, u2, La.scale), cb = hg_cell(u0, u1, u2, Lb.scale);
+        const float2* __restrict__ ba = reinterpret_cast<const float2*>(table) + La.offset;
+        const float2* __restrict__ bb = reinterpret_cast<const float2*>(table) + Lb.offset;
+        float2 va[8], vb[8];
         #pragma unroll
         for (int corner = 0; corner < 8; corner++) {
-            const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
-            v[corner] = __ldg(base + hg_index(cx, cy, cz, L));
+            va[corner] = __ldg(ba + hg_index(ca.c[0] + (corner & 1), ca.c[1] + ((corner >> 1) & 1), ca.c[2] + ((corner >> 2) & 1), La));
+            vb[corner] = __ldg(bb + hg_index(cb.c[0] + (corner & 1), cb.c[1] + ((corner >> 1) & 1), cb.c[2] + ((corner >> 2) & 1), Lb));
         }
-        float f0 = 0.f, f1 = 0.f;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
         #pragma unroll
         for (int corner = 0; corner < 8; corner++) {
-            const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
-            const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
-            const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
-            const float wt = wx * wy * wz;
-            f0 = fmaf(wt, v[corner].x, f0); f1 = fmaf(wt, v[corner].y, f1);
+            const float wa = ((corner & 1) ? ca.w[0] : 1 - ca.w[0]) * ((corner & 2) ? ca.w[1] : 1 - ca.w[1]) * ((corner & 4) ? ca.w[2] : 1 - ca.w[2]);
+            const float wb = ((corner & 1) ? cb.w[0] : 1 - cb.w[0]) * ((corner & 2) ? cb.w[1] : 1 - cb.w[1]) * ((corner & 4) ? cb.w[2] : 1 - cb.w[2]);
+            a0 = fmaf(wa, va[corner].x, a0); a1 = fmaf(wa, va[corner].y, a1);
+            b0 = fmaf(wb, vb[corner].x, b0); b1 = fmaf(wb, vb[corner].y, b1);
         }
-        f[2 * i] = f0; f[2 * i + 1] = f1;
+        f[2 * i] = a0; f[2 * i + 1] = a1;
+        f[2 * i + 2] = two ? b0 : 0.f; f[2 * i + 3] = two ? b1 : 0.f;
     }
 }
 
@@ -760,29 +764,7 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
                 const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
                 // gather first (registers), then wait for the A1 buffer to be released by the previous evaluation's layer-1 MMAs
                 float f[16];
-                #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; continue; }
-                    const LevelSm L = lv[l0 + i];
-                    const CellW cw = hg_cell(u0, u1, u2, L.scale);
-                    const float2* __restrict__ base = reinterpret_cast<const float2*>(a.table) + L.offset;
-                    float2 v[8];
-                    #pragma unroll
-                    for (int corner = 0; corner < 8; corner++) {
-                        const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
-                        v[corner] = __ldg(base + hg_index(cx, cy, cz, L));
-                    }
-                    float f0 = 0.f, f1 = 0.f;
-                    #pragma unroll
-                    for (int corner = 0; corner < 8; corner++) {
-                        const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
-                        const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
-                        const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
-                        const float wt = wx * wy * wz;
-                        f0 = fmaf(wt, v[corner].x, f0); f1 = fmaf(wt, v[corner].y, f1);
-                    }
-                    f[2 * i] = f0; f[2 * i + 1] = f1;
-                }
+                gather16(a.table, lv, l0, lcount, u0, u1, u2, f);
                 if (it > 0) tc::mbar_wait(a1_empty, (it - 1) & 1);
                 #pragma unroll
                 for (int i = 0; i < 8; i++) {

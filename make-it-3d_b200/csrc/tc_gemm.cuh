@@ -53,6 +53,7 @@ struct GemmParams {
     int epi_mode;
     float alpha;                 // scales the accumulator before bias
     int m_valid;                 // rows >= m_valid (per batch) are not stored
+    int m_tiles, n_tiles, num_tiles;   // persistent tile loop: tile t -> n_blk = t % n_tiles, m_blk = (t / n_tiles) % m_tiles, z = t / (n_tiles * m_tiles)
 };
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -151,8 +152,8 @@ template <int BLOCK_N> struct Cfg {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
-    static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256;
+    static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator stages: epilogue(i) overlaps mainloop(i+1)
+    static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 512;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -166,16 +167,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     uint8_t* tiles = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)C::kStages * C::kStageBytes);
     uint64_t* empty_bar = full_bar + C::kStages;
-    uint64_t* tmem_full_bar = empty_bar + C::kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + C::kStages;            // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x, n_blk = blockIdx.y, z = blockIdx.z;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a); prefetch_tmap(&map_b);
         for (int s = 0; s < C::kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -188,33 +189,36 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
-            int cw = 0, ch = 0, cn = 0;
-            if (p.conv) {
-                const int hw = p.conv_H * p.conv_W;
-                cn = m0 / hw; const int rem = m0 - cn * hw;
-                ch = rem / p.conv_W; cw = rem - ch * p.conv_W;
-            }
-            const int az0 = p.a_z1 > 0 ? z % p.a_z1 : 0, az1 = p.a_z1 > 0 ? z / p.a_z1 : 0;
-            const int bz0 = p.b_batched ? (p.b_z1 > 0 ? z % p.b_z1 : 0) : 0, bz1 = p.b_batched ? (p.b_z1 > 0 ? z / p.b_z1 : 0) : 0;
-            for (int kb = 0; kb < p.num_k_blocks; kb++) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = tiles + (size_t)stage * C::kStageBytes;
-                uint8_t* sb = sa + C::kABytes;
-                mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int n_blk = t % p.n_tiles, rest = t / p.n_tiles, m_blk = rest % p.m_tiles, z = rest / p.m_tiles;
+                const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+                int cw = 0, ch = 0, cn = 0;
                 if (p.conv) {
-                    const int tap = kb / p.cin_blocks, cc = kb - tap * p.cin_blocks;
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    tma_load_4d(&map_a, &full_bar[stage], sa, cc * BLOCK_K, cw + kx - 1, ch + ky - 1, cn);
-                } else {
-                    tma_load_4d(&map_a, &full_bar[stage], sa, kb * BLOCK_K, m0, az0, az1);
+                    const int hw = p.conv_H * p.conv_W;
+                    cn = m0 / hw; const int rem = m0 - cn * hw;
+                    ch = rem / p.conv_W; cw = rem - ch * p.conv_W;
                 }
-                if (p.b_mn) {
-                    #pragma unroll
-                    for (int nb = 0; nb < BLOCK_N / 64; nb++) tma_load_4d(&map_b, &full_bar[stage], sb + nb * 8192, n0 + nb * 64, kb * BLOCK_K, 0, 0);
-                } else
-                tma_load_4d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0, bz0, bz1);
-                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                const int az0 = p.a_z1 > 0 ? z % p.a_z1 : 0, az1 = p.a_z1 > 0 ? z / p.a_z1 : 0;
+                const int bz0 = p.b_batched ? (p.b_z1 > 0 ? z % p.b_z1 : 0) : 0, bz1 = p.b_batched ? (p.b_z1 > 0 ? z / p.b_z1 : 0) : 0;
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = tiles + (size_t)stage * C::kStageBytes;
+                    uint8_t* sb = sa + C::kABytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                    if (p.conv) {
+                        const int tap = kb / p.cin_blocks, cc = kb - tap * p.cin_blocks;
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        tma_load_4d(&map_a, &full_bar[stage], sa, cc * BLOCK_K, cw + kx - 1, ch + ky - 1, cn);
+                    } else {
+                        tma_load_4d(&map_a, &full_bar[stage], sa, kb * BLOCK_K, m0, az0, az1);
+                    }
+                    if (p.b_mn) {
+                        #pragma unroll
+                        for (int nb = 0; nb < BLOCK_N / 64; nb++) tma_load_4d(&map_b, &full_bar[stage], sb + nb * 8192, n0 + nb * 64, kb * BLOCK_K, 0, 0);
+                    } else
+                    tma_load_4d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0, bz0, bz1);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -222,86 +226,104 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.b_mn);
             int stage = 0; uint32_t phase = 0;
-            for (int kb = 0; kb < p.num_k_blocks; kb++) {
-                mbar_wait(&full_bar[stage], phase);
+            int it = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
+                const int as = it & 1;
+                mbar_wait(&tmem_empty_bar[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator stage
                 tc_fence_after();
-                const uint32_t sa = smem_u32(tiles + (size_t)stage * C::kStageBytes);
-                const uint64_t da = make_sw128_desc(sa), db = p.b_mn ? make_sw128_desc_mn(sa + C::kABytes, 8192u) : make_sw128_desc(sa + C::kABytes);
-                #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-                    // advancing K inside the 128B swizzle atom = +32 B on the start address (>>4 => +2);
-                    // MN-major B: K runs over rows, 16 rows = 2048 B (>>4 => +128)
-                    umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(p.b_mn ? 128 * k : 2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + (size_t)stage * C::kStageBytes);
+                    const uint64_t da = make_sw128_desc(sa), db = p.b_mn ? make_sw128_desc_mn(sa + C::kABytes, 8192u) : make_sw128_desc(sa + C::kABytes);
+                    #pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                        // advancing K inside the 128B swizzle atom = +32 B on the start address (>>4 => +2);
+                        // MN-major B: K runs over rows, 16 rows = 2048 B (>>4 => +128)
+                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(p.b_mn ? 128 * k : 2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
-                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                umma_commit(&tmem_full_bar[as]);               // accumulator complete
             }
-            umma_commit(tmem_full_bar);                    // accumulator complete
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> HBM =====================
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;               // accumulator row == tile row
-        const int m = m_blk * BLOCK_M + row;
-        const bool row_ok = m < p.m_valid;
-        const size_t zoff = (size_t)(z % p.out_z1) * p.out_s_lo + (size_t)(z / p.out_z1) * p.out_s_hi;
-        const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(((long long)z * p.M + m) / p.rows_per_group) * p.N : nullptr;
-        #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            const int n0 = n_blk * BLOCK_N + c0;
-            float f[32];
-            #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                float x = __uint_as_float(v[i]) * p.alpha;
-                if (p.bias) x += __ldg(p.bias + n0 + i);
-                if (rb) x += __ldg(rb + n0 + i);
-                f[i] = x;
-            }
-            if (!row_ok) continue;
-            if (p.epi_mode == EPI_GEGLU) {
-                // weight rows were interleaved (value, gate) at plan time: out[:, n/2] = value * gelu(gate)
-                __half* o = p.out + zoff + (size_t)m * p.ldc + (n0 >> 1);
-                __align__(16) __half h[16];
+        int it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
+            const int n_blk = t % p.n_tiles, rest = t / p.n_tiles, m_blk = rest % p.m_tiles, z = rest / p.m_tiles;
+            const int as = it & 1;
+            mbar_wait(&tmem_full_bar[as], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const int m = m_blk * BLOCK_M + row;
+            const bool row_ok = m < p.m_valid;
+            const size_t zoff = (size_t)(z % p.out_z1) * p.out_s_lo + (size_t)(z / p.out_z1) * p.out_s_hi;
+            const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(((long long)z * p.M + m) / p.rows_per_group) * p.N : nullptr;
+            #pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v);
+                const int n0 = n_blk * BLOCK_N + c0;
+                float f[32];
                 #pragma unroll
-                for (int i = 0; i < 16; i++) h[i] = __float2half_rn(f[2 * i] * gelu_erf(f[2 * i + 1]));
-                *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
-                *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(h + 8);
-            } else if (p.epi_mode == EPI_TRANSPOSED) {
-                // out[z][n][m]: lanes hold consecutive m -> each store instruction writes 64 contiguous bytes per n
-                __half* o = p.out + zoff + (size_t)n0 * p.ldc + m;
-                #pragma unroll
-                for (int i = 0; i < 32; i++) o[(size_t)i * p.ldc] = __float2half_rn(f[i]);
-            } else {
-                if (p.residual) {
-                    const __half* r = p.residual + zoff + (size_t)m * p.ld_res + n0;
+                for (int i = 0; i < 32; i++) {
+                    float x = __uint_as_float(v[i]) * p.alpha;
+                    if (p.bias) x += __ldg(p.bias + n0 + i);
+                    if (rb) x += __ldg(rb + n0 + i);
+                    f[i] = x;
+                }
+                if (!row_ok) continue;
+                if (p.epi_mode == EPI_GEGLU) {
+                    // weight rows were interleaved (value, gate) at plan time: out[:, n/2] = value * gelu(gate)
+                    __half* o = p.out + zoff + (size_t)m * p.ldc + (n0 >> 1);
+                    __align__(16) __half h[16];
                     #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r) + q);
-                        const __half* rh = reinterpret_cast<const __half*>(&rv);
+                    for (int i = 0; i < 16; i++) h[i] = __float2half_rn(f[2 * i] * gelu_erf(f[2 * i + 1]));
+                    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+                    *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(h + 8);
+                } else if (p.epi_mode == EPI_TRANSPOSED) {
+                    // out[z][n][m]: lanes hold consecutive m -> each store instruction writes 64 contiguous bytes per n
+                    __half* o = p.out + zoff + (size_t)n0 * p.ldc + m;
+                    #pragma unroll
+                    for (int i = 0; i < 32; i++) o[(size_t)i * p.ldc] = __float2half_rn(f[i]);
+                } else {
+                    if (p.residual) {
+                        const __half* r = p.residual + zoff + (size_t)m * p.ld_res + n0;
                         #pragma unroll
-                        for (int i = 0; i < 8; i++) f[8 * q + i] += __half2float(rh[i]);
+                        for (int q = 0; q < 4; q++) {
+                            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r) + q);
+                            const __half* rh = reinterpret_cast<const __half*>(&rv);
+                            #pragma unroll
+                            for (int i = 0; i < 8; i++) f[8 * q + i] += __half2float(rh[i]);
+                        }
+                    }
+                    if (p.out_f32) {
+                        float* o = p.out_f32 + zoff + (size_t)m * p.ldc + n0;
+                        #pragma unroll
+                        for (int q = 0; q < 8; q++) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    } else {
+                        __half* o = p.out + zoff + (size_t)m * p.ldc + n0;
+                        __align__(16) __half h[32];
+                        #pragma unroll
+                        for (int i = 0; i < 32; i++) h[i] = __float2half_rn(f[i]);
+                        #pragma unroll
+                        for (int q = 0; q < 4; q++) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(h)[q];
                     }
                 }
-                if (p.out_f32) {
-                    float* o = p.out_f32 + zoff + (size_t)m * p.ldc + n0;
-                    #pragma unroll
-                    for (int q = 0; q < 8; q++) reinterpret_cast<float4*>(o)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                } else {
-                    __half* o = p.out + zoff + (size_t)m * p.ldc + n0;
-                    __align__(16) __half h[32];
-                    #pragma unroll
-                    for (int i = 0; i < 32; i++) h[i] = __float2half_rn(f[i]);
-                    #pragma unroll
-                    for (int q = 0; q < 4; q++) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(h)[q];
-                }
+            }
+            // release this accumulator stage to the MMA warp (one arrive per epilogue warp)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[as])) : "memory");
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, C::kTmemCols); }
 }

@@ -68,8 +68,13 @@ inline int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmPar
         MI3D_CHECK(cudaFuncSetAttribute(k_tc_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::kSmemBytes));
         attr = true;
     }
-    dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, p.N / BN, batch);
-    k_tc_gemm<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, p);
+    GemmParams q = p;
+    q.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M; q.n_tiles = p.N / BN; q.num_tiles = q.m_tiles * q.n_tiles * batch;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int resident = (Cfg<BN>::kSmemBytes <= 110 * 1024) ? 2 : 1;       // persistent grid: one (or two) CTAs per SM loop over the tiles
+    const int grid = q.num_tiles < sms * resident ? q.num_tiles : sms * resident;
+    k_tc_gemm<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ma, mb, q);
     return (int)cudaGetLastError();
 }
 

@@ -77,19 +77,27 @@ def test_implicit_conv3x3_matches_fp32_reference(L, Nimg, H, W, Cin, Cout):
     assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("N,K", [(64, 32), (64, 64), (32, 64), (16, 64), (64, 128), (32, 128)])
-def test_tf32_split_tiles(L, mode, N, K):
-    """Hand-written kind::tf32 tiles (field kernels): 3-term split must be fp32-class; K-major and MN-major descriptors."""
-    g = torch.Generator(device="cuda").manual_seed(N + K + mode)
-    if mode == 0:
-        a = torch.randn(128, K, device="cuda", generator=g); b = torch.randn(N, K, device="cuda", generator=g); ref = a.double() @ b.double().t()
-    elif mode == 1:
-        a = torch.randn(K, 128, device="cuda", generator=g); b = torch.randn(K, N, device="cuda", generator=g); ref = a.double().t() @ b.double()
-    else:
-        a = torch.randn(128, K, device="cuda", generator=g); b = torch.randn(K, N, device="cuda", generator=g); ref = a.double() @ b.double()
+def test_tf32_split_tiles(L, N, K):
+    """Hand-written kind::tf32 tiles of the field FORWARD kernel (K-major operands): the 3-term split must be fp32-class.
+    (kind::tf32 has no working MN-major form -- tools/explore_mn.py -- which is why the backward uses bf16 tiles.)"""
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    a = torch.randn(128, K, device="cuda", generator=g); b = torch.randn(N, K, device="cuda", generator=g); ref = a.double() @ b.double().t()
     d = torch.empty(128, N, device="cuda")
-    L.check(L.lib().mi3d_tf32_tile_test(L.ptr(a), L.ptr(b), L.ptr(d), C.c_int(N), C.c_int(K), C.c_int(mode), L.stream()), "tf32_tile_test")
+    L.check(L.lib().mi3d_tf32_tile_test(L.ptr(a), L.ptr(b), L.ptr(d), C.c_int(N), C.c_int(K), C.c_int(0), L.stream()), "tf32_tile_test")
     torch.cuda.synchronize()
     err = (d.double() - ref).abs().max().item()
-    assert err < 2e-5 * max(1.0, ref.abs().max().item()), (mode, N, K, err)     # plain tf32 would be ~1e-2
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), (N, K, err)     # plain tf32 would be ~1e-2
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (128, 64, 256, 64), (256, 128, 128, 128), (128, 256, 64, 256), (1024, 64, 512, 64)])
+def test_gemm_mn_major_b_operand(L, M, N, K, bn):
+    """16-bit MN-major B operand (B given as [K][N]): the descriptor form the field backward relies on for dgrad / wgrad."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    bt = (torch.randn(K, N, device="cuda", generator=g) / K ** 0.5).half()
+    out = torch.zeros(M, N, device="cuda")
+    L.check(L.lib().mi3d_gemm_f16_bt(L.ptr(a), L.ptr(bt), L.ptr(out), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(bn), L.stream()), "gemm_f16_bt")
+    torch.cuda.synchronize()
+    ref = a.float() @ bt.float()
+    assert (out - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
