@@ -151,6 +151,29 @@ __device__ __forceinline__ void scatter_level_agg(float* __restrict__ gtable, co
     }
 }
 
+// single-level-at-a-time variant (8 loads in flight): lower register pressure, used by the backward's prefetch
+__device__ __forceinline__ void gather16s(const float* __restrict__ table, const LevelSm* __restrict__ lv, int l0, int lcount,
+                                          float u0, float u1, float u2, float (&f)[16]) {
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; continue; }
+        const LevelSm L = lv[l0 + i];
+        const CellW cw = hg_cell(u0, u1, u2, L.scale);
+        const float2* __restrict__ base = reinterpret_cast<const float2*>(table) + L.offset;
+        float2 v[8];
+        #pragma unroll
+        for (int corner = 0; corner < 8; corner++)
+            v[corner] = __ldg(base + hg_index(cw.c[0] + (corner & 1), cw.c[1] + ((corner >> 1) & 1), cw.c[2] + ((corner >> 2) & 1), L));
+        float f0 = 0.f, f1 = 0.f;
+        #pragma unroll
+        for (int corner = 0; corner < 8; corner++) {
+            const float wt = ((corner & 1) ? cw.w[0] : 1 - cw.w[0]) * ((corner & 2) ? cw.w[1] : 1 - cw.w[1]) * ((corner & 4) ? cw.w[2] : 1 - cw.w[2]);
+            f0 = fmaf(wt, v[corner].x, f0); f1 = fmaf(wt, v[corner].y, f1);
+        }
+        f[2 * i] = f0; f[2 * i + 1] = f1;
+    }
+}
+
 // gather + trilinear blend of levels [l0, l0 + lcount) (lcount <= 8) of point u into f[2i], f[2i+1].
 // Levels are processed in PAIRS: 16 independent 8-byte loads are in flight per thread before any is consumed (the kernels
 // are bound by gather latency, not by issue slots or L1 wavefronts -- ncu: long_scoreboard dominates).
@@ -565,7 +588,7 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint
 }
 }  // namespace fwdtc
 
-__global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdArgs a) {
+__global__ void __maxnreg__(152) k_field_fwd_tc(const FwdArgs a) {
     using namespace fwdtc;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -1065,7 +1088,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 }  // namespace bwdtc
 
-__global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdArgs a) {
+__global__ void __maxnreg__(152) k_field_bwd_tc(const BwdArgs a) {
     using namespace bwdtc;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -1278,24 +1301,17 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 #pragma unroll
                 for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
             }
-            float f[16], fn[16];
-            {
-                float p[3];
-                eval_pos(0, x, xp, a.bound, p);
-                gather16(a.table, lv, l0, lcount, (p[0] + a.bound) / inv2b, (p[1] + a.bound) / inv2b, (p[2] + a.bound) / inv2b, f);
-            }
-            for (int e = 0; e < e_end; e++, it++) {
-                const uint32_t par = it & 1;
-                float p[3];
-                eval_pos(e, x, xp, a.bound, p);
-                const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
-                // A1 is free once WG1 of the previous evaluation retired (d4_full), which this thread waited for when it scattered
+            // Software pipeline over the evaluations of this tile:
+            //   write E(e+1) as soon as chain(e) has retired (d4) and BEFORE scattering dEnc(e), so that the MMA / epilogue chain of
+            //   e+1 overlaps the scatter of e and the gather of e+2.
+            float f[16];
+            auto write_E = [&](const float (&ff)[16]) {
                 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     if (i >= lcount) continue;
                     const int k = 2 * (l0 + i);
                     __nv_bfloat16 h0, m0, q0, h1, m1b, q1;
-                    split3(f[2 * i], h0, m0, q0); split3(f[2 * i + 1], h1, m1b, q1);
+                    split3(ff[2 * i], h0, m0, q0); split3(ff[2 * i + 1], h1, m1b, q1);
                     const uint32_t o = oE + sw_off16(r, k);
                     *reinterpret_cast<__nv_bfloat162*>(sm + o) = __halves2bfloat162(h0, h1);
                     *reinterpret_cast<__nv_bfloat162*>(sm + o + kTile) = __halves2bfloat162(m0, m1b);
@@ -1303,11 +1319,23 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 }
                 tc::fence_proxy_async();
                 mbar_arrive(a1_full);
+            };
+            {
+                float p[3];
+                eval_pos(0, x, xp, a.bound, p);
+                gather16s(a.table, lv, l0, lcount, (p[0] + a.bound) / inv2b, (p[1] + a.bound) / inv2b, (p[2] + a.bound) / inv2b, f);
+                write_E(f);            // E is free: this thread waited for d4 of the previous evaluation (or it is the first one)
+            }
+            for (int e = 0; e < e_end; e++, it++) {
+                const uint32_t par = it & 1;
+                float p[3];
+                eval_pos(e, x, xp, a.bound, p);
+                const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
                 // prefetch the next evaluation's gather while the MMA / epilogue chain of this one runs
                 if (e + 1 < e_end) {
                     float pn[3];
                     eval_pos(e + 1, x, xp, a.bound, pn);
-                    gather16(a.table, lv, l0, lcount, (pn[0] + a.bound) / inv2b, (pn[1] + a.bound) / inv2b, (pn[2] + a.bound) / inv2b, fn);
+                    gather16s(a.table, lv, l0, lcount, (pn[0] + a.bound) / inv2b, (pn[1] + a.bound) / inv2b, (pn[2] + a.bound) / inv2b, f);
                 }
                 // db2: column sums of dZ2
                 tc::mbar_wait(a3_full, par);
@@ -1335,12 +1363,14 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     ab1 += sacc;
                 }
                 mbar_arrive(r4_done);
-                // dEnc (this thread's 16 columns of its row) straight from TMEM, then scatter
+                // dEnc (this thread's 16 columns of its row) straight from TMEM into registers
                 tc::mbar_wait(d4_full, par);
                 tc::tc_fence_after();
                 uint32_t g[16];
                 tmem_ld16(lane_addr + cG1 + (uint32_t)(2 * l0), g);
                 tc::tc_fence_before();
+                // chain(e) has retired: E is free -> hand the next evaluation to the MMA warp before scattering this one
+                if (e + 1 < e_end) write_E(f);
                 #pragma unroll 1
                 for (int i = 0; i < lcount; i++) {
                     float g0 = 0.f, g1 = 0.f;
@@ -1350,8 +1380,6 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     // aggregate where a cell spans several march steps (2 / scale  >  ~1.5 dt_min): levels 0..7 of the reference grid
                     scatter_level_agg(a.g_table, L, u0, u1, u2, g0, g1, in_range, L.scale < 200.f, lane);
                 }
-                #pragma unroll
-                for (int i = 0; i < 16; i++) f[i] = fn[i];
             }
         }
         atomicAdd(a.g_mlp.b2 + cj, ab2);
