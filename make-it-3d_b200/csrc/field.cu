@@ -588,7 +588,8 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint
 }
 }  // namespace fwdtc
 
-__global__ void __maxnreg__(136) k_field_fwd_tc(const FwdArgs a) {
+// 13 warps are allocated as 16 for the register file -> 128 registers per thread is the hard ceiling for this CTA shape
+__global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdArgs a) {
     using namespace fwdtc;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -1088,7 +1089,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 }  // namespace bwdtc
 
-__global__ void __maxnreg__(136) k_field_bwd_tc(const BwdArgs a) {
+__global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdArgs a) {
     using namespace bwdtc;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
