@@ -162,7 +162,11 @@ int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_h
 int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
                         const mi3d_field_cfg* cfg, const float* tape, const float* grad_sigmas, const float* grad_rgbs,
                         const float* grad_normals, const float* grad_loss_orient, const float* grad_loss_smooth,
-                        float* grad_table, const mi3d_mlp_grad* grad_mlp, mi3d_stream_t stream);
+                        float* grad_table, const mi3d_mlp_grad* grad_mlp, void* workspace, mi3d_stream_t stream);
+/* workspace (nullable): mi3d_field_backward_workspace_bytes() bytes of scratch.  When given, the backward runs as a three-kernel
+ * pipeline per chunk of 1 048 576 samples (full-occupancy gather -> tensor-core chain -> full-occupancy warp-aggregated scatter);
+ * when NULL everything stays in one kernel (slower: the gather/scatter warps are starved). */
+size_t mi3d_field_backward_workspace_bytes(void);
 
 /* Replaces NeRFRenderer.update_extra_state (nerf/renderer.py:587-637): density_grid [C,H^3] EMA-max update from the
  * field at jittered cell centres, mean density (device scalar out), bitfield repack.  jitter: [C,H^3,3] U[0,1) or NULL

@@ -49,7 +49,7 @@ SYMBOLS = [
     "mi3d_composite_rays_train_forward", "mi3d_composite_rays_train_backward",
     "mi3d_march_rays", "mi3d_composite_rays",
     "mi3d_hashgrid_make", "mi3d_hashgrid_forward", "mi3d_hashgrid_backward",
-    "mi3d_field_grid_ctas", "mi3d_field_forward", "mi3d_field_backward",
+    "mi3d_field_grid_ctas", "mi3d_field_forward", "mi3d_field_backward", "mi3d_field_backward_workspace_bytes",
     "mi3d_density_grid_workspace_bytes", "mi3d_density_grid_update", "mi3d_version",
     "mi3d_gemm_f16", "mi3d_conv3x3_f16", "mi3d_tf32_tile_test", "mi3d_gemm_f16_bt",
     "mi3d_sd_workspace_bytes", "mi3d_sd_create", "mi3d_sd_destroy", "mi3d_sd_num_params", "mi3d_sd_param_name", "mi3d_sd_param_numel",
@@ -76,6 +76,7 @@ def lib():
         _lib.mi3d_version.restype = C.c_char_p
         _lib.mi3d_march_rays_train_workspace_bytes.restype = C.c_size_t
         _lib.mi3d_density_grid_workspace_bytes.restype = C.c_size_t
+        _lib.mi3d_field_backward_workspace_bytes.restype = C.c_size_t
         for name in ("mi3d_sd_workspace_bytes", "mi3d_sd_weight_bytes"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_size_t

@@ -867,6 +867,8 @@ struct BwdArgs {
     const float* tape;
     const float* g_sigmas; const float* g_rgbs; const float* g_normals; const float* g_loss_orient; const float* g_loss_smooth;
     float* g_table; mi3d_mlp_grad g_mlp;
+    // split pipeline (encode kernel -> tensor-core chain kernel -> scatter kernel) over tiles [tile0, tile1): see k_bwd_encode
+    float* enc_buf; float* denc_buf; uint32_t tile0, tile1;
 };
 
 // d(loss)/d(h) of the 13 evaluations of one sample from the upstream gradients and the forward tape (sigma0, albedo, tap sigmas):
@@ -1048,6 +1050,87 @@ __global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
     }
 }
 
+__device__ __forceinline__ void load16(const float* __restrict__ src, float (&f)[16]) {
+    #pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+        f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Split backward pipeline.  ncu showed the single-kernel tensor-core backward bound by the ~8 gather/scatter warps it can
+// afford next to 200 KB of operand tiles (issue 14 %, tensor pipe 3 %, long_scoreboard dominant).  The hash-grid gather and
+// the RED scatter are embarrassingly parallel over (sample, level), so they run as their own full-occupancy kernels around the
+// chain kernel and exchange encodings / encoding-gradients through a per-chunk HBM buffer (128 B per evaluation each way:
+// ~1.4 GB per backward at 128x128, i.e. ~0.2 ms of HBM time for ~2x less wall time).
+//   k_bwd_encode : block = (tile, evaluation), thread = (row, group of 4 levels)  -> enc_buf[tile][e][row][32]
+//   k_field_bwd_tc (ext mode): loads enc, runs the MMA chain, stores d(enc) -> denc_buf
+//   k_bwd_scatter: same mapping as encode, warp-aggregated REDs (lanes = consecutive samples of a ray)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bwd_e_end(const BwdArgs& a, uint32_t m_pad) {
+    const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
+    const float Go = (a.g_loss_orient && a.n_evals >= 7) ? *a.g_loss_orient : 0.f;
+    const float Gs = (a.g_loss_smooth && a.n_evals > 7) ? *a.g_loss_smooth : 0.f;
+    const bool need_ptaps = Gs != 0.f;
+    const bool need_taps = a.n_evals >= 7 && (need_ptaps || Go != 0.f || lit || a.g_normals != nullptr);
+    return !need_taps ? 1 : (need_ptaps ? 13 : 7);
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(512, 2) k_bwd_enc_scatter(const BwdArgs a) {
+    __shared__ LevelSm lv[16];
+    if (threadIdx.x < 16) {
+        LevelSm L; const int l = threadIdx.x;
+        if (l < (int)a.hg.n_levels) {
+            L.offset = a.hg.offsets[l]; L.size = a.hg.sizes[l]; L.res = a.hg.ress[l]; L.scale = a.hg.scales[l];
+            L.hashed = (uint64_t)L.res * L.res * L.res > (uint64_t)L.size ? 1u : 0u;
+        } else { L.offset = 0; L.size = 8; L.res = 2; L.scale = 1.f; L.hashed = 0; }
+        lv[l] = L;
+    }
+    __syncthreads();
+    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
+    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
+    const int e_end = bwd_e_end(a, m_pad);
+    const int r = threadIdx.x & (T - 1), lg = threadIdx.x >> 7, lane = threadIdx.x & 31;   // levels 4 lg .. 4 lg + 3
+    const float inv2b = 2.f * a.bound;
+    // persistent grid-stride loop over (tile, evaluation) work items of this chunk
+    for (uint32_t w = blockIdx.x;; w += gridDim.x) {
+        const uint32_t tile = a.tile0 + w / (uint32_t)e_end;
+        const int e = (int)(w % (uint32_t)e_end);
+        if (tile >= a.tile1 || (uint64_t)tile * T >= m_pad) break;
+        const uint32_t row = tile * T + r;
+        const bool in_range = row < m_pad, real = row < M;
+        float x[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
+        if (real) { x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2]; }
+        if (e >= 7 && in_range) {
+            float z[3];
+            if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
+            else gauss_pair(a.seed, row, 1u, z);
+            #pragma unroll
+            for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
+        }
+        float p[3];
+        eval_pos(e, x, xp, a.bound, p);
+        const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
+        const size_t base = ((size_t)(tile - a.tile0) * 13 + e) * (T * 32) + (size_t)r * 32 + 8 * lg;
+        if (!SCATTER) {
+            float f[16];
+            gather16(a.table, lv, 4 * lg, 4, u0, u1, u2, f);
+            float4* dst = reinterpret_cast<float4*>(a.enc_buf + base);
+            dst[0] = make_float4(f[0], f[1], f[2], f[3]); dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.denc_buf + base)), g1 = __ldg(reinterpret_cast<const float4*>(a.denc_buf + base) + 1);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const LevelSm L = lv[4 * lg + i];
+                scatter_level_agg(a.g_table, L, u0, u1, u2, g[2 * i], g[2 * i + 1], in_range, L.scale < 200.f, lane);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // backward, tensor-core variant.  Same roles as k_field_fwd_tc; per evaluation the MMA thread runs
 //   F1: D1 = Enc W1^T          F2: D2 = H1 W2^T                               (recompute, K-major operands)
@@ -1091,6 +1174,10 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdArgs a) {
     using namespace bwdtc;
+    {   // chunk entirely past the (device-side) sample count: nothing to do
+        const uint32_t M0 = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
+        if ((uint64_t)a.tile0 * T >= padded_rows(M0, a.align, a.cap)) return;
+    }
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     float* b1s = reinterpret_cast<float*>(sm + oMisc);          // 64
@@ -1158,7 +1245,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
         // persistent partial sums over this warp's rows: lane j owns columns j and j+32 of dW3[o][.] ; db3 on lane o
         float aw3[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, ab3 = 0.f;
-        for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+        for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
             const bool in_range = row < m_pad, real = row < M;
             float d[3] = {0.f, 0.f, 0.f};
@@ -1289,8 +1376,9 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         // column sums for db2 / db1: this thread sums column cj over rows [rs, rs + 32)
         const int cj = et & 63, rs = (et >> 6) * 32;
+        const bool ext = a.enc_buf != nullptr;
         float ab2 = 0.f, ab1 = 0.f;
-        for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+        for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
             const bool in_range = row < m_pad, real = row < M;
             float x[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
@@ -1324,7 +1412,8 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
             {
                 float p[3];
                 eval_pos(0, x, xp, a.bound, p);
-                gather16s(a.table, lv, l0, lcount, (p[0] + a.bound) / inv2b, (p[1] + a.bound) / inv2b, (p[2] + a.bound) / inv2b, f);
+                if (ext) load16(a.enc_buf + ((size_t)(tile - a.tile0) * 13 + 0) * (T * 32) + (size_t)r * 32 + 16 * half, f);
+                else gather16s(a.table, lv, l0, lcount, (p[0] + a.bound) / inv2b, (p[1] + a.bound) / inv2b, (p[2] + a.bound) / inv2b, f);
                 write_E(f);            // E is free: this thread waited for d4 of the previous evaluation (or it is the first one)
             }
             for (int e = 0; e < e_end; e++, it++) {
@@ -1336,7 +1425,8 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 if (e + 1 < e_end) {
                     float pn[3];
                     eval_pos(e + 1, x, xp, a.bound, pn);
-                    gather16s(a.table, lv, l0, lcount, (pn[0] + a.bound) / inv2b, (pn[1] + a.bound) / inv2b, (pn[2] + a.bound) / inv2b, f);
+                    if (ext) load16(a.enc_buf + ((size_t)(tile - a.tile0) * 13 + (e + 1)) * (T * 32) + (size_t)r * 32 + 16 * half, f);
+                    else gather16s(a.table, lv, l0, lcount, (pn[0] + a.bound) / inv2b, (pn[1] + a.bound) / inv2b, (pn[2] + a.bound) / inv2b, f);
                 }
                 // db2: column sums of dZ2
                 tc::mbar_wait(a3_full, par);
@@ -1372,6 +1462,11 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 tc::tc_fence_before();
                 // chain(e) has retired: E is free -> hand the next evaluation to the MMA warp before scattering this one
                 if (e + 1 < e_end) write_E(f);
+                if (ext) {
+                    float4* dst = reinterpret_cast<float4*>(a.denc_buf + ((size_t)(tile - a.tile0) * 13 + e) * (T * 32) + (size_t)r * 32 + 16 * half);
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = make_float4(__uint_as_float(g[4 * q]), __uint_as_float(g[4 * q + 1]), __uint_as_float(g[4 * q + 2]), __uint_as_float(g[4 * q + 3]));
+                } else
                 #pragma unroll 1
                 for (int i = 0; i < lcount; i++) {
                     float g0 = 0.f, g1 = 0.f;
@@ -1395,7 +1490,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
             const Operand W1k{sbase + oW1, 8192u, 16u, 0}, W1m{sbase + oW1, 8192u, 8192u, 1};
             const Operand W2k{sbase + oW2, 8192u, 16u, 0}, W2m{sbase + oW2, 8192u, 8192u, 1};
             uint32_t accW = 0;
-            for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
+            for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
                 for (int e = 0; e < e_end; e++, it++) {
                     const uint32_t par = it & 1;
                     tc::mbar_wait(a1_full, par); tc::tc_fence_after();
@@ -1604,7 +1699,10 @@ int mi3d_hashgrid_backward(const float* x, uint32_t E, const float* grad_out, co
 // MI3D_FIELD_TC=0 selects the FFMA forward kernel (kept for A/B measurements); default is the tcgen05 3xTF32 kernel
 static bool use_tc() { static int v = -1; if (v < 0) { const char* e = getenv("MI3D_FIELD_TC"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
 
+constexpr uint32_t kBwdChunkTiles = 8192;     // 1 048 576 samples per chunk: 2 x 1.74 GB of encoding / gradient staging
 static bool use_tc_bwd() { static int v = -1; if (v < 0) { const char* e = getenv("MI3D_FIELD_TC_BWD"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
+
+size_t mi3d_field_backward_workspace_bytes(void) { return (size_t)2 * kBwdChunkTiles * 13 * T * 32 * sizeof(float); }
 
 int mi3d_field_grid_ctas(int backward) { return num_sms() * (backward ? 1 : 2); }
 
@@ -1634,7 +1732,7 @@ int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_h
 int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
                         const mi3d_field_cfg* cfg, const float* tape, const float* grad_sigmas, const float* grad_rgbs,
                         const float* grad_normals, const float* grad_loss_orient, const float* grad_loss_smooth,
-                        float* grad_table, const mi3d_mlp_grad* grad_mlp, mi3d_stream_t stream) {
+                        float* grad_table, const mi3d_mlp_grad* grad_mlp, void* workspace, mi3d_stream_t stream) {
     if (!io || !hg || !mlp || !cfg || !tape || !grad_table || !grad_mlp) return MI3D_ERR_ARG;
     if (cfg->n_evals != 1 && cfg->n_evals != 7 && cfg->n_evals != 13) return MI3D_ERR_ARG;
     if (hg->n_levels * 2 != D_IN) return MI3D_ERR_ARG;
@@ -1648,8 +1746,23 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     a.tape = tape; a.g_sigmas = grad_sigmas; a.g_rgbs = grad_rgbs; a.g_normals = grad_normals;
     a.g_loss_orient = grad_loss_orient; a.g_loss_smooth = grad_loss_smooth;
     a.g_table = grad_table; a.g_mlp = *grad_mlp;
-    if (use_tc_bwd()) k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
-    else k_field_bwd<<<mi3d_field_grid_ctas(1), NT, smem_bytes(true), (cudaStream_t)stream>>>(a);
+    a.enc_buf = nullptr; a.denc_buf = nullptr; a.tile0 = 0; a.tile1 = 0xFFFFFFFFu;
+    if (use_tc_bwd()) {
+        if (workspace && hg->n_levels == 16) {
+            // split pipeline, chunk by chunk (the sample count lives on the device: chunks past it return immediately)
+            a.enc_buf = (float*)workspace; a.denc_buf = a.enc_buf + (size_t)kBwdChunkTiles * 13 * T * 32;
+            const uint32_t total_tiles = (io->cap + T - 1) / T;
+            for (uint32_t t0 = 0; t0 < total_tiles; t0 += kBwdChunkTiles) {
+                a.tile0 = t0; a.tile1 = t0 + kBwdChunkTiles;
+                k_bwd_enc_scatter<false><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a);
+                k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
+                k_bwd_enc_scatter<true><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a);
+                if (!io->counter && (uint64_t)(t0 + kBwdChunkTiles) * T >= io->m_fixed) break;
+            }
+        } else {
+            k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
+        }
+    } else k_field_bwd<<<mi3d_field_grid_ctas(1), NT, smem_bytes(true), (cudaStream_t)stream>>>(a);
     MI3D_RETURN_LAUNCH();
 }
 

@@ -31,6 +31,17 @@ def _timed(name, info, fn):
     return r
 
 
+_BWD_SCRATCH = {}
+
+
+def bwd_scratch(device):
+    """per-device staging buffer of the split backward pipeline (mi3d_field_backward_workspace_bytes), allocated once"""
+    key = str(device)
+    if key not in _BWD_SCRATCH:
+        _BWD_SCRATCH[key] = torch.empty(L.lib().mi3d_field_backward_workspace_bytes(), dtype=torch.uint8, device=device)
+    return _BWD_SCRATCH[key]
+
+
 def make_hashgrid(n_levels=16, base_resolution=16, per_level_scale=1.3819128274917603, log2_hashmap_size=19):
     hg = L.HashGrid()
     L.check(L.lib().mi3d_hashgrid_make(C.c_uint32(n_levels), C.c_uint32(base_resolution), C.c_double(per_level_scale),
@@ -124,7 +135,7 @@ class _FieldEval(Function):
                 g_normals = None
             L.check(L.lib().mi3d_field_backward(C.byref(io), L.ptr(table), C.byref(ctx.hg), C.byref(mlp), C.byref(cf), L.ptr(tape),
                                                 L.ptr(g_sigmas), L.ptr(g_rgbs), L.ptr(g_normals), L.ptr(g_lo), L.ptr(g_ls),
-                                                L.ptr(g_table), C.byref(gm), L.stream()), "field_backward")
+                                                L.ptr(g_table), C.byref(gm), L.ptr(bwd_scratch(table.device)), L.stream()), "field_backward")
         return (g_table, *g_ws, None, None, None, None, None, None, None)
 
 
@@ -244,7 +255,7 @@ class _RenderTrain(Function):
         full = (g_lo is not None) or (g_ls is not None) or ctx.cfg["shading"] != "albedo"
         _timed("k_field_bwd", dict(n_evals=ctx.cfg["n_evals"], N=N, full=full), lambda: L.check(lib.mi3d_field_backward(
             C.byref(io), L.ptr(table), C.byref(ctx.hg), C.byref(mlp), C.byref(cf), L.ptr(ws.tape), L.ptr(ws.g_sigmas), L.ptr(ws.g_rgbs),
-            C.c_void_p(0), L.ptr(g_lo), L.ptr(g_ls), L.ptr(g_table), C.byref(gm), L.stream()), "field_backward"))
+            C.c_void_p(0), L.ptr(g_lo), L.ptr(g_ls), L.ptr(g_table), C.byref(gm), L.ptr(bwd_scratch(table.device)), L.stream()), "field_backward"))
         return (g_table, *g_P) + (None,) * 13
 
 
