@@ -218,7 +218,7 @@ def run_ours(args):
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             step(0, False)
             torch.cuda.synchronize()
-        mine = ("k_field", "k_march", "k_composite", "k_tc_gemm", "sdk::", "sd::k_", "k_loss_finalize", "k_near_far", "k_packbits", "k_grid")
+        mine = ("k_field", "k_bwd", "k_march", "k_composite", "k_tc_gemm", "sdk::", "sd::k_", "k_loss_finalize", "k_near_far", "k_packbits", "k_grid")
         launches_per_step = sum(1 for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA and any(m in ev.name for m in mine))
     except Exception:
         launches_per_step = None
@@ -227,10 +227,16 @@ def run_ours(args):
     time.sleep(0.3)
     ms = timed(args.steps, False, args.warmup)
     # ---- per-kernel live timing of the dominant kernels (CUDA events on the launching stream) ----
+    import ctypes as C
+    L = importlib.import_module("make-it-3d_b200._lib")
     field_ops.PROFILE = []
-    for s in range(3):
+    L.check(L.lib().mi3d_sd_profile(guidance.engine.h, C.c_int(1), None, None), "sd_profile")
+    n_prof = 3
+    for s in range(n_prof):
         step(args.warmup + s, False)
     torch.cuda.synchronize()
+    gemm_ms, gemm_n = C.c_float(0), C.c_int(0)
+    L.check(L.lib().mi3d_sd_profile(guidance.engine.h, C.c_int(0), C.byref(gemm_ms), C.byref(gemm_n)), "sd_profile")
     prof_rows = field_ops.PROFILE
     field_ops.PROFILE = None
     ms_e2e = timed(args.steps, True, args.warmup)
@@ -251,32 +257,49 @@ def run_ours(args):
         "gpu_launches": (launches_per_step * args.steps) if launches_per_step is not None else None,
         "clocks": clock_info,
     }
-    # roofline of the dominant kernel (largest share of the step): the fused field backward
+    # roofline of the dominant kernel = the tcgen05 tile kernel k_tc_gemm (every conv / linear / attention product of the U-Net
+    # and the VAE: the largest share of the step).  achieved = algorithmic FLOPs of one step (1.608 + 1.117 + 1.117
+    # TFLOP) / summed duration of its launches in that step, timed live with CUDA events around each launch.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     per_kernel = {}
     for name, s, e, info in prof_rows:
         key = name + ("_full" if info.get("full") else ("_image" if name == "k_field_bwd" else ""))
         per_kernel.setdefault(key, []).append(s.elapsed_time(e))
     m_pad = M + 128 - M % 128
-    fb = per_kernel.get("k_field_bwd_full", [])
-    traffic = None
+    summary = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_summary.json"))).get("k_field_bwd_full", {}).get("dram_bytes_per_launch")
+        summary = json.load(open(os.path.join(ROOT, "profiles", "r1_summary.json")))
     except Exception:
         pass
-    if fb:
-        t_ms = float(np.median(fb))
-        alg_bytes = 13 * m_pad * 2048 + N * 16          # 2048 B / eval (fp32 gradient RMW of 128 corners) + ray grads
-        line["roofline"] = {"kernel": "k_field_bwd (13 evals/sample)", "bound": "hbm", "achieved": round(alg_bytes / (t_ms * 1e-3) / 1e9, 1),
-                            "peak": hbm, "unit": "GB/s", "frac": round(alg_bytes / (t_ms * 1e-3) / 1e9 / hbm, 4), "traffic": traffic,
-                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                            "ms_per_launch": round(t_ms, 3), "algorithmic_bytes_per_launch": int(alg_bytes),
-                            "other_kernels_ms": {k: round(float(np.median(v)), 3) for k, v in per_kernel.items()}}
+    gemm_ms_step = gemm_ms.value / n_prof
+    flops = 3.842e12
+    line["roofline"] = {
+        "kernel": "tc::k_tc_gemm<64|128|256> (tcgen05.mma/TMEM/TMA tile kernel; all launches of one step)", "bound": "tensor",
+        "achieved": round(flops / (gemm_ms_step * 1e-3) / 1e12, 1), "peak": tf_peak, "unit": "TFLOP/s",
+        "frac": round(flops / (gemm_ms_step * 1e-3) / 1e12 / tf_peak, 4),
+        "traffic": summary.get("k_tc_gemm", {}).get("dram_bytes_per_launch"),
+        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured; kernel timed inside a long step)" if peaks else "fallback 1400 TFLOP/s (of fallback)",
+        "ms_per_step": round(gemm_ms_step, 3), "launches_per_step": gemm_n.value // n_prof, "algorithmic_flops_per_step": flops,
+    }
+    # second roofline: the render kernels against the HBM roofline the north_star names (algorithmic bytes of SURVEY 8d;
+    # these kernels are really bound by L1 gather / RED-atomic throughput)
+    rk = {k: round(float(np.median(v)), 3) for k, v in per_kernel.items()}
+    fwd_ms = rk.get("k_field_fwd")
+    bwd_ms = rk.get("k_field_bwd_full")
+    line["roofline_render"] = {"bound": "hbm", "peak": hbm, "unit": "GB/s", "kernels_ms": rk,
+                               "traffic": {k: summary.get(k, {}).get("dram_bytes_per_launch") for k in ("k_field_fwd_tc", "k_bwd_enc_scatter", "k_field_bwd_tc")}}
+    if fwd_ms:
+        ab = 13 * m_pad * 1024 + N * 44 + 262144
+        line["roofline_render"]["fwd"] = {"algorithmic_bytes": int(ab), "achieved": round(ab / (fwd_ms * 1e-3) / 1e9, 1), "frac": round(ab / (fwd_ms * 1e-3) / 1e9 / hbm, 4)}
+    if bwd_ms:
+        ab = 13 * m_pad * 2048 + N * 16
+        line["roofline_render"]["bwd"] = {"algorithmic_bytes": int(ab), "achieved": round(ab / (bwd_ms * 1e-3) / 1e9, 1), "frac": round(ab / (bwd_ms * 1e-3) / 1e9 / hbm, 4)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:

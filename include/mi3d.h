@@ -249,6 +249,9 @@ int mi3d_sd_encode_backward(mi3d_sd_t h, const float* grad_latents, const float*
  * text_embeddings fp32 [2,77,cross_dim] (uncond first); noise_pred / grad (nullable) fp32 [1,4,h,w]. */
 int mi3d_sd_unet_sds(mi3d_sd_t h, const float* latents, const float* noise, const long long* t, const float* alphas_cumprod,
                      const float* text_embeddings, float guidance_scale, float* noise_pred, float* grad, mi3d_stream_t stream);
+/* live timing of the tensor-core tile kernel: enable=1 starts recording CUDA events around every launch; enable=0 stops and
+ * returns the summed kernel time (ms) and launch count (HOST pointers; synchronises on the recorded events). */
+int mi3d_sd_profile(mi3d_sd_t h, int enable, float* gemm_ms_host, int* launches_host);
 /* debug tap: device pointer + size of a named intermediate ("unet.mid", "vae.grad_in", ...) */
 int mi3d_sd_debug_tensor(mi3d_sd_t h, const char* name, void** ptr, size_t* bytes);
 

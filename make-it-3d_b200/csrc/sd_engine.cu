@@ -52,6 +52,17 @@ struct Engine {
     T4 unet_in; float* unet_out = nullptr; __half* ctx16 = nullptr; float* temb = nullptr; long long* t_dev = nullptr;
     T4 vae_in; float* vae_moments = nullptr; float* vae_gmoments = nullptr; __half* vae_gin = nullptr;
     int ctx_pad = 128;
+    // optional live timing of the tensor-core tile kernel (bench.py roofline leg): CUDA events around every k_tc_gemm launch
+    bool profile = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; size_t prof_used = 0;
+    int timed_launch(const CUtensorMap& ma, const CUtensorMap& mb, const tc::GemmParams& p, int bn, int batch, cudaStream_t st) {
+        if (!profile) return tc::launch(ma, mb, p, bn, batch, st);
+        if (prof_used == prof_events.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); prof_events.push_back({a, b}); }
+        auto& ev = prof_events[prof_used++];
+        cudaEventRecord(ev.first, st);
+        const int r = tc::launch(ma, mb, p, bn, batch, st);
+        cudaEventRecord(ev.second, st);
+        return r;
+    }
 
     void* alloc(size_t bytes) {
         off = (off + 1023) & ~(size_t)1023;
@@ -107,7 +118,7 @@ struct Engine {
         p.out = o.p16; p.out_f32 = o.p32; p.ldc = o.ldc; p.out_z1 = o.z1; p.out_s_lo = o.s_lo; p.out_s_hi = o.s_hi;
         p.bias = e.bias; p.row_bias = e.row_bias; p.rows_per_group = e.rows_per_group; p.residual = e.residual; p.ld_res = e.ld_res;
         p.epi_mode = e.mode; p.alpha = e.alpha; p.m_valid = (int)a.rows;
-        push([ma, mb, p, bn, batch](cudaStream_t st) { return tc::launch(ma, mb, p, bn, batch, st); });
+        push([this, ma, mb, p, bn, batch](cudaStream_t st) { return timed_launch(ma, mb, p, bn, batch, st); });
     }
 
     // y[M,N] = x[M,K] W[N,K]^T (+bias) (+residual)
@@ -138,7 +149,7 @@ struct Engine {
         p.a_z1 = 1; p.b_z1 = 1; p.b_batched = 0; p.out = y.p; p.ldc = Cout; p.out_z1 = 1;
         p.bias = bias; p.row_bias = row_bias; p.rows_per_group = x.h * x.w; p.residual = residual; p.ld_res = Cout;
         p.epi_mode = tc::EPI_PLAIN; p.alpha = 1.f; p.m_valid = (int)M;
-        push([ma, mb, p, bn](cudaStream_t st) { return tc::launch(ma, mb, p, bn, 1, st); });
+        push([this, ma, mb, p, bn](cudaStream_t st) { return timed_launch(ma, mb, p, bn, 1, st); });
     }
 
     struct GN { double* stats; const float* gamma; const float* beta; float eps; int silu; T4 x; int G; };
@@ -907,6 +918,25 @@ int mi3d_sd_load_param(mi3d_sd_t h, int i, const float* src, const float* partne
         }
     }
     return (int)cudaGetLastError();
+}
+
+// enable != 0: start timing every tensor-core tile launch with CUDA events; enable == 0: stop, synchronise the events and
+// return the accumulated kernel milliseconds and launch count since the last enable
+int mi3d_sd_profile(mi3d_sd_t h, int enable, float* gemm_ms, int* launches) {
+    if (!h) return MI3D_ERR_ARG;
+    sd::Engine& e = h->e;
+    if (enable) { e.profile = true; e.prof_used = 0; return MI3D_OK; }
+    e.profile = false;
+    float total = 0.f;
+    for (size_t i = 0; i < e.prof_used; i++) {
+        float ms = 0.f;
+        MI3D_CHECK(cudaEventSynchronize(e.prof_events[i].second));
+        MI3D_CHECK(cudaEventElapsedTime(&ms, e.prof_events[i].first, e.prof_events[i].second));
+        total += ms;
+    }
+    if (gemm_ms) *gemm_ms = total;
+    if (launches) *launches = (int)e.prof_used;
+    return MI3D_OK;
 }
 
 int mi3d_sd_debug_tensor(mi3d_sd_t h, const char* name, void** ptr, size_t* bytes) {
