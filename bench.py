@@ -239,7 +239,12 @@ def run_ours(args):
     L.check(L.lib().mi3d_sd_profile(guidance.engine.h, C.c_int(0), C.byref(gemm_ms), C.byref(gemm_n)), "sd_profile")
     prof_rows = field_ops.PROFILE
     field_ops.PROFILE = None
+    for s in range(2):                      # untimed: first-use allocations of the host-input staging path
+        step(s, True)
     ms_e2e = timed(args.steps, True, args.warmup)
+    if os.environ.get("MI3D_BENCH_ABAB"):        # diagnostic: is the e2e/device gap the copies or the order (clocks)?
+        a2 = timed(args.steps, False, args.warmup); b2 = timed(args.steps, True, args.warmup); a3 = timed(args.steps, False, args.warmup)
+        print(f"[abab] dev {ms / args.steps:.3f} e2e {ms_e2e / args.steps:.3f} dev {a2 / args.steps:.3f} e2e {b2 / args.steps:.3f} dev {a3 / args.steps:.3f} ms/step", file=sys.stderr)
     clock_info = clocks.stop()
     ws = list(model._workspaces.values())[0]
     M = int(ws.counter[0])

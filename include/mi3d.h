@@ -184,10 +184,23 @@ int mi3d_density_grid_update(float* density_grid, uint8_t* density_bitfield, uin
 /* The one tensor-core tile kernel (tcgen05.mma + TMEM accumulators + TMA operand staging) exposed directly:
  *   out[M,N] = alpha * A[M,K] . B[N,K]^T + bias[N] (+ residual[M,N]);  A, B fp16 K-major; out fp16 or fp32.
  * Stands in for the cuBLAS GEMM under every nn.Linear of diffusers' UNet2DConditionModel / AutoencoderKL
- * (nerf/sd.py:146, :217).  M % 128 == 0, K % 64 == 0, N % block_n == 0 (block_n in {64,128,256}; 0 = auto).
+ * (nerf/sd.py:146, :217).  M % 128 == 0, K % 64 == 0, N % block_n == 0 (block_n in {64,128,160,256}; 0 = auto).
  * epi_mode: 0 plain, 1 GEGLU (rows of B interleaved value/gate; out is [M, N/2]), 2 transposed store (out is [N, M]). */
 int mi3d_gemm_f16(const void* a, const void* b, void* out, int out_is_f32, int M, int N, int K, int block_n, float alpha,
                   const float* bias, const void* residual, int epi_mode, mi3d_stream_t stream);
+
+/* Split-K form used for the deep U-Net levels (M = 128 .. 512 rows, K up to 23 040): `splits` K-ranges per output tile run on
+ * different SMs and meet by fp32 RED in ws ([M][N] floats, zeroed inside); bias / residual / fp16 conversion happen in a
+ * second pass.  fp16 output, plain epilogue only. */
+int mi3d_gemm_f16_splitk(const void* a, const void* b, void* out, int M, int N, int K, int block_n, int splits, float alpha,
+                         const float* bias, const void* residual, void* ws, mi3d_stream_t stream);
+
+/* Fused multi-head attention, head_dim 64 (stands in for diffusers' attention processor inside BasicTransformerBlock.attn1 /
+ * .attn2, nerf/sd.py:146): o = softmax(q k^T / 8) v per (batch, head), scores kept in TMEM / shared memory.
+ * q [B*T, ldq], k and v [B*Tk, ldk / ldv], o [B*T, ldo], fp16, head h at columns [64h, 64h+64); only the first Tk_valid keys of
+ * every batch take part (77 of the 128 padded text rows for cross attention).  All ld % 8 == 0. */
+int mi3d_flash_attn_f16(const void* q, const void* k, const void* v, void* o, int B, int T, int Tk, int Tk_valid, int heads,
+                        int ldq, int ldk, int ldv, int ldo, mi3d_stream_t stream);
 
 /* Implicit-GEMM 3x3 stride-1 pad-1 convolution on the same kernel (stands in for the cuDNN conv under diffusers'
  * ResnetBlock2D / Downsample2D / Upsample2D): x [N,H,W,Cin] fp16 NHWC, w [Cout][3][3][Cin] fp16, y [N,H,W,Cout] fp16. */

@@ -51,7 +51,7 @@ SYMBOLS = [
     "mi3d_hashgrid_make", "mi3d_hashgrid_forward", "mi3d_hashgrid_backward",
     "mi3d_field_grid_ctas", "mi3d_field_forward", "mi3d_field_backward", "mi3d_field_backward_workspace_bytes",
     "mi3d_density_grid_workspace_bytes", "mi3d_density_grid_update", "mi3d_version",
-    "mi3d_gemm_f16", "mi3d_conv3x3_f16", "mi3d_tf32_tile_test", "mi3d_gemm_f16_bt",
+    "mi3d_gemm_f16", "mi3d_gemm_f16_splitk", "mi3d_flash_attn_f16", "mi3d_conv3x3_f16", "mi3d_tf32_tile_test", "mi3d_gemm_f16_bt",
     "mi3d_sd_workspace_bytes", "mi3d_sd_create", "mi3d_sd_destroy", "mi3d_sd_num_params", "mi3d_sd_param_name", "mi3d_sd_param_numel",
     "mi3d_sd_param_shape", "mi3d_sd_load_param", "mi3d_sd_encode", "mi3d_sd_encode_backward", "mi3d_sd_unet_sds", "mi3d_sd_debug_tensor", "mi3d_sd_profile",
 ]

@@ -1,0 +1,248 @@
+// attn.cuh -- fused multi-head attention (softmax(Q K^T / sqrt(d)) V) for the SD-2.0 U-Net transformer blocks, d = 64.
+//
+// Replaces the three-launch form (batched QK^T tile GEMM -> softmax over the materialised [B*heads, T, Tk] fp16 score tensor ->
+// batched PV tile GEMM) that stood in for diffusers' attention processor under nerf/sd.py:146.  At 64x64 latents one layer's
+// score tensor is 335 MB; here scores never leave the SM: S lives in TMEM, P goes registers -> swizzled shared memory -> tcgen05.
+//
+// One CTA = one 128-query tile of one (batch, head).  192 threads:
+//   warps 0-3  softmax / output owners: thread r owns query row r (TMEM lane r): running max, running sum, O[64] in registers
+//   warp 4     TMA producer: Q once, K double-buffered, V single-buffered (4D maps: d, token, head, batch; 128B swizzle)
+//   warp 5     tcgen05 issuer:  S = Q K_j^T (M128 N128 K64, both K-major)  ->  TMEM cols [0,128)
+//                               PV = P_j V_j (M128 N64 K128, P K-major from smem, V MN-major as loaded) -> TMEM cols [128,192)
+// Per key block j:   MMA1(j) -> s_full -> softmax(j): two TMEM passes (row max, then exp2 / sum / fp16 P into smem) -> p_full
+//                    -> MMA2(j), MMA1(j+1) -> pv_full -> O = O * alpha + PV -> pv_empty.
+// 97 KB shared memory and 256 TMEM columns per CTA: two CTAs per SM cover each other's softmax / MMA bubbles.
+#pragma once
+#include "tc_host.cuh"
+
+namespace attn {
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kTile = 16384;                                 // 128 rows x 128 B
+constexpr size_t kSmemBytes = 1024 + 6 * (size_t)kTile + 256;   // Q, K0, K1, V, P0, P1 + barriers
+constexpr uint32_t kTmemCols = 256;
+
+struct Params {
+    int T;              // queries per (batch, head)
+    int kv_valid;       // keys per (batch, head) that take part (77 of the 128 padded context rows for cross attention)
+    int ldo;            // row stride of o (elements)
+    float scale_log2e;  // (1 / sqrt(d)) * log2(e)
+    __half* o;          // [B*T, ldo], head h at column h * 64
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+static __global__ void __launch_bounds__(kThreads, 2)
+k_flash_attn(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+             const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + kTile;            // two stages
+    uint8_t* sV = sK + 2 * kTile;
+    uint8_t* sP = sV + kTile;            // two 64-key atoms [128 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTile);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;         // [2]
+    uint64_t* k_empty = bars + 3;        // [2]
+    uint64_t* v_full = bars + 5;
+    uint64_t* v_empty = bars + 6;
+    uint64_t* s_full = bars + 7;
+    uint64_t* p_full = bars + 8;
+    uint64_t* pv_full = bars + 9;
+    uint64_t* pv_empty = bars + 10;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, batch = blockIdx.z;
+    const int nkv = (p.kv_valid + 127) >> 7;
+
+    if (warp == 4 && lane == 0) {
+        prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+        mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(pv_full, 1); mbar_init(pv_empty, 128);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, kTile);
+            tma_load_4d(&map_q, q_full, sQ, 0, q0, head, batch);
+            for (int j = 0; j < nkv; j++) {
+                const int st = j & 1;
+                mbar_wait(&k_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&k_full[st], kTile);
+                tma_load_4d(&map_k, &k_full[st], sK + st * kTile, 0, j * 128, head, batch);
+                mbar_wait(v_empty, ((uint32_t)j & 1u) ^ 1u);
+                mbar_arrive_expect_tx(v_full, kTile);
+                tma_load_4d(&map_v, v_full, sV, 0, j * 128, head, batch);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== tcgen05 issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_f16(128, 128, 0), idesc_pv = make_idesc_f16(128, 64, 1);
+            const uint64_t dq = make_sw128_desc(smem_u32(sQ));
+            const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+            auto issue_s = [&](int j) {
+                const int st = j & 1;
+                mbar_wait(&k_full[st], ((uint32_t)j >> 1) & 1u);
+                tc_fence_after();
+                const uint64_t dk = make_sw128_desc(smem_u32(sK + st * kTile));
+                #pragma unroll
+                for (int k = 0; k < 4; k++) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(s_full);
+                umma_commit(&k_empty[st]);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nkv; j++) {
+                mbar_wait(p_full, (uint32_t)j & 1u);              // S(j) drained from TMEM, P(j) in shared memory
+                mbar_wait(v_full, (uint32_t)j & 1u);
+                if (j > 0) mbar_wait(pv_empty, (uint32_t)(j - 1) & 1u);
+                tc_fence_after();
+                const uint64_t dv = make_sw128_desc_mn(smem_u32(sV), 8192u);
+                #pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint64_t dp = make_sw128_desc(smem_u32(sP + (k >> 2) * kTile)) + (uint64_t)(2 * (k & 3));
+                    umma_f16(tmem_pv, dp, dv + (uint64_t)(128 * k), idesc_pv, k > 0 ? 1u : 0u);
+                }
+                umma_commit(pv_full);
+                umma_commit(v_empty);
+                if (j + 1 < nkv) issue_s(j + 1);
+            }
+        }
+    } else {
+        // ===================== softmax / output owners: thread = query row =====================
+        const int r = warp * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const float c = p.scale_log2e;
+        float m = -INFINITY, l = 0.f;
+        float O[64];
+        #pragma unroll
+        for (int i = 0; i < 64; i++) O[i] = 0.f;
+        uint8_t* prow = sP + r * 128;
+        const int rx = r & 7;
+        for (int j = 0; j < nkv; j++) {
+            mbar_wait(s_full, (uint32_t)j & 1u);
+            tc_fence_after();
+            const int kbase = j * 128;
+            const bool edge = kbase + 128 > p.kv_valid;
+            float mx = -INFINITY;
+            #pragma unroll 1
+            for (int cc = 0; cc < 4; cc++) {
+                uint32_t v[32];
+                tmem_ld32(t_row + (uint32_t)(cc * 32), v);
+                #pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    float s = __uint_as_float(v[i]);
+                    if (edge && kbase + cc * 32 + i >= p.kv_valid) s = -INFINITY;
+                    mx = fmaxf(mx, s);
+                }
+            }
+            const float m_new = fmaxf(m, mx);
+            const float mc = m_new * c;
+            const float alpha = exp2f(m * c - mc);                 // first block: exp2(-inf) = 0
+            float rs = 0.f;
+            #pragma unroll 1
+            for (int cc = 0; cc < 4; cc++) {
+                uint32_t v[32];
+                tmem_ld32(t_row + (uint32_t)(cc * 32), v);
+                uint8_t* atom = prow + (cc >> 1) * kTile;
+                #pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    __align__(16) __half2 h2[4];
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        float s0 = __uint_as_float(v[g * 8 + 2 * i]), s1 = __uint_as_float(v[g * 8 + 2 * i + 1]);
+                        float p0 = exp2f(s0 * c - mc), p1 = exp2f(s1 * c - mc);
+                        if (edge) {
+                            const int col = kbase + cc * 32 + g * 8 + 2 * i;
+                            if (col >= p.kv_valid) p0 = 0.f;
+                            if (col + 1 >= p.kv_valid) p1 = 0.f;
+                        }
+                        h2[i] = __floats2half2_rn(p0, p1);
+                        // the sum runs over the fp16-rounded probabilities the tensor core will actually multiply
+                        const float2 pr = __half22float2(h2[i]);
+                        rs += pr.x + pr.y;
+                    }
+                    const int chunk = (cc & 1) * 4 + g;            // 16-byte chunk inside the 128-byte row of this atom
+                    *reinterpret_cast<uint4*>(atom + ((chunk ^ rx) << 4)) = *reinterpret_cast<const uint4*>(h2);
+                }
+            }
+            l = l * alpha + rs;
+            m = m_new;
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(p_full);
+            mbar_wait(pv_full, (uint32_t)j & 1u);
+            tc_fence_after();
+            #pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+                uint32_t v[32];
+                tmem_ld32(t_row + 128u + (uint32_t)(cc * 32), v);
+                #pragma unroll
+                for (int i = 0; i < 32; i++) O[cc * 32 + i] = O[cc * 32 + i] * alpha + __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            mbar_arrive(pv_empty);
+        }
+        if (q0 + r < p.T) {
+            const float inv = 1.f / l;
+            __half* dst = p.o + ((size_t)batch * p.T + q0 + r) * p.ldo + head * 64;
+            #pragma unroll
+            for (int g = 0; g < 8; g++) {
+                __align__(16) __half2 h2[4];
+                #pragma unroll
+                for (int i = 0; i < 4; i++) h2[i] = __floats2half2_rn(O[g * 8 + 2 * i] * inv, O[g * 8 + 2 * i + 1] * inv);
+                *reinterpret_cast<uint4*>(dst + g * 8) = *reinterpret_cast<const uint4*>(h2);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+struct Maps { CUtensorMap q, k, v; };
+
+// token matrices: x[(b * tokens + t) * ld + h * 64 + i]
+inline int make_maps(Maps* m, const __half* q, long long ldq, const __half* k, long long ldk, const __half* v, long long ldv,
+                     int B, int T, int Tk, int heads) {
+    const uint32_t box[4] = {64, 128, 1, 1};
+    auto one = [&](CUtensorMap* map, const __half* base, long long ld, int tokens) {
+        const uint64_t dims[4] = {64, (uint64_t)tokens, (uint64_t)heads, (uint64_t)B};
+        const uint64_t str[4] = {2, (uint64_t)ld * 2, 128, (uint64_t)tokens * (uint64_t)ld * 2};
+        return make_map_f16(map, base, dims, str, box);
+    };
+    int r = one(&m->q, q, ldq, T);
+    if (r) return r;
+    r = one(&m->k, k, ldk, Tk);
+    if (r) return r;
+    return one(&m->v, v, ldv, Tk);
+}
+
+static inline int launch(const Maps& m, __half* o, long long ldo, int B, int T, int kv_valid, int heads, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        MI3D_CHECK(cudaFuncSetAttribute(k_flash_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        attr = true;
+    }
+    if (kv_valid < 1 || T < 1) return MI3D_ERR_ARG;
+    Params p; p.T = T; p.kv_valid = kv_valid; p.ldo = (int)ldo; p.scale_log2e = 0.125f * 1.4426950408889634f; p.o = o;
+    dim3 grid((unsigned)((T + 127) / 128), (unsigned)heads, (unsigned)B);
+    k_flash_attn<<<grid, kThreads, kSmemBytes, st>>>(m.q, m.k, m.v, p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace attn

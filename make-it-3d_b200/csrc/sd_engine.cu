@@ -11,6 +11,8 @@
 // Activations: NHWC fp16.  Accumulation / statistics: fp32 (fp64 group sums).  Weights: fp16 copies of the fp32
 // diffusers parameters, re-laid-out at load time (conv OIHW -> O,ky,kx,I ; GEGLU rows interleaved ; dgrad copies).
 #include <functional>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -19,6 +21,7 @@
 #include "../../include/mi3d.h"
 #include "sd_kernels.cuh"
 #include "tc_host.cuh"
+#include "attn.cuh"
 
 namespace sd {
 
@@ -52,14 +55,22 @@ struct Engine {
     T4 unet_in; float* unet_out = nullptr; __half* ctx16 = nullptr; float* temb = nullptr; long long* t_dev = nullptr;
     T4 vae_in; float* vae_moments = nullptr; float* vae_gmoments = nullptr; __half* vae_gin = nullptr;
     int ctx_pad = 128;
+    float* splitk_ws = nullptr; size_t splitk_elems = 0;      // fp32 scratch shared by all split-K GEMMs (they run one at a time)
     // optional live timing of the tensor-core tile kernel (bench.py roofline leg): CUDA events around every k_tc_gemm launch
     bool profile = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; size_t prof_used = 0;
+    struct ProfShape { int M, N, K, bn, splits, conv, batch, epi; }; std::vector<ProfShape> prof_shapes;
+    int do_launch(const CUtensorMap& ma, const CUtensorMap& mb, const tc::GemmParams& p, int bn, int batch, cudaStream_t st) {
+        if (p.splits > 1) return tc::launch_splitk(ma, mb, p, bn, p.splits, splitk_ws, st);
+        return tc::launch(ma, mb, p, bn, batch, st);
+    }
     int timed_launch(const CUtensorMap& ma, const CUtensorMap& mb, const tc::GemmParams& p, int bn, int batch, cudaStream_t st) {
-        if (!profile) return tc::launch(ma, mb, p, bn, batch, st);
+        if (!profile) return do_launch(ma, mb, p, bn, batch, st);
         if (prof_used == prof_events.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); prof_events.push_back({a, b}); }
+        if (prof_shapes.size() < prof_events.size()) prof_shapes.resize(prof_events.size());
+        prof_shapes[prof_used] = {p.M, p.N, p.K, bn, p.splits, p.conv, batch, p.epi_mode};
         auto& ev = prof_events[prof_used++];
         cudaEventRecord(ev.first, st);
-        const int r = tc::launch(ma, mb, p, bn, batch, st);
+        const int r = do_launch(ma, mb, p, bn, batch, st);
         cudaEventRecord(ev.second, st);
         return r;
     }
@@ -106,8 +117,13 @@ struct Engine {
     void gemm(const Mat& a, const Mat& b, int N, const Out& o, const Epi& e, int batch = 1, bool b_batched = false) {
         if (dry) return;
         const long long mt = (a.rows + 127) / 128;
-        const int bn = tc::pick_block_n(N, mt * batch, num_sms);
+        int bn = tc::pick_block_n(N, mt * batch, num_sms);
         if (bn == 0 || a.K % 64) { err = MI3D_ERR_ARG; return; }
+        int splits = 1;
+        if (batch == 1 && e.mode == tc::EPI_PLAIN && o.p16 && a.rows % 128 == 0 && (size_t)a.rows * N <= splitk_elems) {
+            if (N % 128 == 0 && mt * (N / 128) * 2 <= num_sms) bn = 128;            // few, fat tiles + split-K beats many thin tiles
+            splits = tc::plan_splits(mt * (N / bn), a.K / 64, num_sms);
+        }
         CUtensorMap ma, mb;
         int r = tc::make_map_matrix(&ma, a.p, a.K, a.rows, a.ld, 128, a.z1, a.sz1, a.z2, a.sz2);
         if (!r) r = tc::make_map_matrix(&mb, b.p, b.K, b.rows, b.ld, bn, b.z1, b.sz1, b.z2, b.sz2);
@@ -117,7 +133,7 @@ struct Engine {
         p.a_z1 = a.z1; p.b_z1 = b.z1; p.b_batched = b_batched ? 1 : 0;
         p.out = o.p16; p.out_f32 = o.p32; p.ldc = o.ldc; p.out_z1 = o.z1; p.out_s_lo = o.s_lo; p.out_s_hi = o.s_hi;
         p.bias = e.bias; p.row_bias = e.row_bias; p.rows_per_group = e.rows_per_group; p.residual = e.residual; p.ld_res = e.ld_res;
-        p.epi_mode = e.mode; p.alpha = e.alpha; p.m_valid = (int)a.rows;
+        p.epi_mode = e.mode; p.alpha = e.alpha; p.m_valid = (int)a.rows; p.splits = splits;
         push([this, ma, mb, p, bn, batch](cudaStream_t st) { return timed_launch(ma, mb, p, bn, batch, st); });
     }
 
@@ -137,8 +153,13 @@ struct Engine {
         const long long M = x.rows();
         int bw = x.w < 128 ? x.w : 128, bh = 128 / bw; if (bh > x.h) bh = x.h; const int bn_img = 128 / (bw * bh);
         if (M % 128 || x.c % 64 || bw * bh * bn_img != 128 || x.w % bw || x.h % bh || x.n % bn_img) { err = MI3D_ERR_ARG; return; }
-        const int bn = tc::pick_block_n(Cout, M / 128, num_sms);
+        int bn = tc::pick_block_n(Cout, M / 128, num_sms);
         if (!bn) { err = MI3D_ERR_ARG; return; }
+        int splits = 1;
+        if ((size_t)M * Cout <= splitk_elems) {
+            if (Cout % 128 == 0 && (M / 128) * (Cout / 128) * 2 <= num_sms) bn = 128;
+            splits = tc::plan_splits((M / 128) * (Cout / bn), 9 * (x.c / 64), num_sms);
+        }
         CUtensorMap ma, mb;
         int r = tc::make_map_nhwc(&ma, x.p, x.c, x.w, x.h, x.n, bw, bh, bn_img);
         if (!r) r = tc::make_map_matrix(&mb, w, 9ull * x.c, Cout, 9ull * x.c, bn);
@@ -148,7 +169,7 @@ struct Engine {
         p.conv_H = x.h; p.conv_W = x.w; p.conv_bw = bw; p.conv_bh = bh; p.cin_blocks = x.c / 64;
         p.a_z1 = 1; p.b_z1 = 1; p.b_batched = 0; p.out = y.p; p.ldc = Cout; p.out_z1 = 1;
         p.bias = bias; p.row_bias = row_bias; p.rows_per_group = x.h * x.w; p.residual = residual; p.ld_res = Cout;
-        p.epi_mode = tc::EPI_PLAIN; p.alpha = 1.f; p.m_valid = (int)M;
+        p.epi_mode = tc::EPI_PLAIN; p.alpha = 1.f; p.m_valid = (int)M; p.splits = splits;
         push([this, ma, mb, p, bn](cudaStream_t st) { return timed_launch(ma, mb, p, bn, 1, st); });
     }
 
@@ -253,27 +274,15 @@ struct Engine {
         return out;
     }
 
-    // multi-head attention core on token matrices.  q: [B*T, ldq] (head h at column h*64), k likewise [B*Tk, ldk],
-    // vT: [C][B*Tk] (transposed values).  Writes o [B*T, C].
-    void attention_core(const __half* q, long long ldq, const __half* k, long long ldk, const __half* vT, int B, int T, int Tk, int Tk_valid,
-                        int heads, int d, __half* o, int C) {
-        __half* S = alloc16((size_t)B * heads * T * Tk);
-        {   // S[z] = Q_z K_z^T
-            Mat a{q, ldq, T, d, heads, d, B, (long long)T * ldq};
-            Mat b{k, ldk, Tk, d, heads, d, B, (long long)Tk * ldk};
-            Out oo; oo.p16 = S; oo.ldc = Tk; oo.z1 = heads; oo.s_lo = (long long)T * Tk; oo.s_hi = (long long)heads * T * Tk;
-            Epi e;
-            gemm(a, b, Tk, oo, e, B * heads, true);
-        }
-        softmax(S, (size_t)B * heads * T, Tk, Tk_valid, 1.0f / sqrtf((float)d));
-        {   // O_z = P_z V_z   (B operand = V^T rows h*d.., columns b*Tk..)
-            const long long ldv = (long long)B * Tk;
-            Mat a{S, Tk, T, Tk, heads, (long long)T * Tk, B, (long long)heads * T * Tk};
-            Mat b{vT, ldv, d, Tk, heads, (long long)d * ldv, B, Tk};
-            Out oo; oo.p16 = o; oo.ldc = C; oo.z1 = heads; oo.s_lo = d; oo.s_hi = (long long)T * C;
-            Epi e;
-            gemm(a, b, d, oo, e, B * heads, true);
-        }
+    // multi-head attention core on token matrices (attn.cuh).  q: [B*T, ldq] (head h at column h*64), k / v likewise
+    // [B*Tk, ld]; only the first Tk_valid keys of each batch take part.  Writes o [B*T, C].
+    void attention_core(const __half* q, long long ldq, const __half* k, long long ldk, const __half* v, long long ldv, int B, int T, int Tk,
+                        int Tk_valid, int heads, int d, __half* o, int C) {
+        if (d != 64) { err = MI3D_ERR_ARG; return; }
+        if (dry) return;
+        attn::Maps m;
+        if (int r = attn::make_maps(&m, q, ldq, k, ldk, v, ldv, B, T, Tk, heads)) { err = r; return; }
+        push([=](cudaStream_t st) { return attn::launch(m, o, C, B, T, Tk_valid, heads, st); });
     }
 
     T4 transformer(const std::string& pre, const T4& x, int heads) {
@@ -287,24 +296,24 @@ struct Engine {
         // ---- self attention ----
         __half* ln = alloc16(M * C);
         layernorm(h, M, C, tb + ".norm1", ln);
-        __half* qb = alloc16(M * C); __half* kb = alloc16(M * C); __half* vT = alloc16(M * C);
+        __half* qb = alloc16(M * C); __half* kb = alloc16(M * C); __half* vb = alloc16(M * C);
         linear(ln, M, C, (const __half*)param(tb + ".attn1.to_q.weight", {C, C}, PK_LINEAR).dst, C, qb);
         linear(ln, M, C, (const __half*)param(tb + ".attn1.to_k.weight", {C, C}, PK_LINEAR).dst, C, kb);
-        linear(ln, M, C, (const __half*)param(tb + ".attn1.to_v.weight", {C, C}, PK_LINEAR).dst, C, vT, nullptr, nullptr, tc::EPI_TRANSPOSED);
+        linear(ln, M, C, (const __half*)param(tb + ".attn1.to_v.weight", {C, C}, PK_LINEAR).dst, C, vb);
         __half* ao = alloc16(M * C);
-        attention_core(qb, C, kb, C, vT, B, T, T, T, heads, d, ao, C);
+        attention_core(qb, C, kb, C, vb, C, B, T, T, T, heads, d, ao, C);
         __half* h2 = alloc16(M * C);
         linear(ao, M, C, (const __half*)param(tb + ".attn1.to_out.0.weight", {C, C}, PK_LINEAR).dst, C, h2, pf(tb + ".attn1.to_out.0.bias", {C}), h);
         // ---- cross attention (keys/values from the text context, padded to ctx_pad rows per batch) ----
         __half* ln2 = alloc16(M * C);
         layernorm(h2, M, C, tb + ".norm2", ln2);
         const long long Mc = (long long)B * ctx_pad;
-        __half* q2 = alloc16(M * C); __half* k2 = alloc16(Mc * C); __half* v2T = alloc16(Mc * C);
+        __half* q2 = alloc16(M * C); __half* k2 = alloc16(Mc * C); __half* v2 = alloc16(Mc * C);
         linear(ln2, M, C, (const __half*)param(tb + ".attn2.to_q.weight", {C, C}, PK_LINEAR).dst, C, q2);
         linear(ctx16, Mc, cross, (const __half*)param(tb + ".attn2.to_k.weight", {C, cross}, PK_LINEAR).dst, C, k2);
-        linear(ctx16, Mc, cross, (const __half*)param(tb + ".attn2.to_v.weight", {C, cross}, PK_LINEAR).dst, C, v2T, nullptr, nullptr, tc::EPI_TRANSPOSED);
+        linear(ctx16, Mc, cross, (const __half*)param(tb + ".attn2.to_v.weight", {C, cross}, PK_LINEAR).dst, C, v2);
         __half* ao2 = alloc16(M * C);
-        attention_core(q2, C, k2, C, v2T, B, T, ctx_pad, ucfg.ctx_len, heads, d, ao2, C);
+        attention_core(q2, C, k2, C, v2, C, B, T, ctx_pad, ucfg.ctx_len, heads, d, ao2, C);
         __half* h3 = alloc16(M * C);
         linear(ao2, M, C, (const __half*)param(tb + ".attn2.to_out.0.weight", {C, C}, PK_LINEAR).dst, C, h3, pf(tb + ".attn2.to_out.0.bias", {C}), h2);
         // ---- GEGLU feed-forward ----
@@ -673,6 +682,7 @@ struct Engine {
     int build(bool dry_run) {
         dry = dry_run; off = 0; err = 0; params.clear(); pindex.clear(); unet_ops.clear(); enc_ops.clear(); enc_bwd_ops.clear();
         vres.clear(); vdown.clear(); vorder.clear(); named.clear();
+        splitk_elems = (size_t)2048 * 2560; splitk_ws = alloc32(splitk_elems);       // covers M <= 2048 rows x N <= 2560
         if (ucfg.n_levels > 0) build_unet();
         if (vcfg.n_levels > 0) { build_vae(); build_vae_bwd(); }
         return err;
@@ -928,12 +938,16 @@ int mi3d_sd_profile(mi3d_sd_t h, int enable, float* gemm_ms, int* launches) {
     if (enable) { e.profile = true; e.prof_used = 0; return MI3D_OK; }
     e.profile = false;
     float total = 0.f;
+    const char* dump = getenv("MI3D_SD_PROFILE_DUMP");        // tools/: one line per launch "M N K block_n splits conv batch epi ms"
+    FILE* f = dump ? fopen(dump, "w") : nullptr;
     for (size_t i = 0; i < e.prof_used; i++) {
         float ms = 0.f;
         MI3D_CHECK(cudaEventSynchronize(e.prof_events[i].second));
         MI3D_CHECK(cudaEventElapsedTime(&ms, e.prof_events[i].first, e.prof_events[i].second));
         total += ms;
+        if (f) { const auto& q = e.prof_shapes[i]; fprintf(f, "%d %d %d %d %d %d %d %d %.4f\n", q.M, q.N, q.K, q.bn, q.splits, q.conv, q.batch, q.epi, ms); }
     }
+    if (f) fclose(f);
     if (gemm_ms) *gemm_ms = total;
     if (launches) *launches = (int)e.prof_used;
     return MI3D_OK;

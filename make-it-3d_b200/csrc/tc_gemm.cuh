@@ -53,6 +53,8 @@ struct GemmParams {
     int epi_mode;
     float alpha;                 // scales the accumulator before bias
     int m_valid;                 // rows >= m_valid (per batch) are not stored
+    int splits, kb_per_split;     // split-K: work item t -> (t % splits) K-range, partial sums RED-added (fp32) into splitk_ws[M][N]
+    float* splitk_ws;
     int m_tiles, n_tiles, num_tiles;   // persistent tile loop: tile t -> n_blk = t % n_tiles, m_blk = (t / n_tiles) % m_tiles, z = t / (n_tiles * m_tiles)
 };
 
@@ -148,11 +150,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc_mn(uint32_t smem_addr, uint3
 }
 
 template <int BLOCK_N> struct Cfg {
-    static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 4);   // BN=64: 96 KB -> 2 CTAs/SM
+    static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 4);   // BN=64: 96 KB -> 2 CTAs/SM ; BN=160: 4 x 36 KB
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator stages: epilogue(i) overlaps mainloop(i+1)
+    // two accumulator stages (epilogue(i) overlaps mainloop(i+1)); allocations are powers of two
+    static constexpr int kTmemCols = 2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
     static constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 512;
 };
 
@@ -190,7 +193,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                const int n_blk = t % p.n_tiles, rest = t / p.n_tiles, m_blk = rest % p.m_tiles, z = rest / p.m_tiles;
+                const int sp = t % p.splits, tt = t / p.splits;
+                const int n_blk = tt % p.n_tiles, rest = tt / p.n_tiles, m_blk = rest % p.m_tiles, z = rest / p.m_tiles;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
                 const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
                 int cw = 0, ch = 0, cn = 0;
                 if (p.conv) {
@@ -200,7 +205,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 }
                 const int az0 = p.a_z1 > 0 ? z % p.a_z1 : 0, az1 = p.a_z1 > 0 ? z / p.a_z1 : 0;
                 const int bz0 = p.b_batched ? (p.b_z1 > 0 ? z % p.b_z1 : 0) : 0, bz1 = p.b_batched ? (p.b_z1 > 0 ? z / p.b_z1 : 0) : 0;
-                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = tiles + (size_t)stage * C::kStageBytes;
                     uint8_t* sb = sa + C::kABytes;
@@ -232,7 +237,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 mbar_wait(&tmem_empty_bar[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
-                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                const int sp = t % p.splits;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)stage * C::kStageBytes);
@@ -241,7 +248,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
                         // advancing K inside the 128B swizzle atom = +32 B on the start address (>>4 => +2);
                         // MN-major B: K runs over rows, 16 rows = 2048 B (>>4 => +128)
-                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(p.b_mn ? 128 * k : 2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(p.b_mn ? 128 * k : 2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -255,7 +262,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int row = quarter * 32 + lane;               // accumulator row == tile row
         int it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
-            const int n_blk = t % p.n_tiles, rest = t / p.n_tiles, m_blk = rest % p.m_tiles, z = rest / p.m_tiles;
+            const int tt = t / p.splits;
+            const int n_blk = tt % p.n_tiles, rest = tt / p.n_tiles, m_blk = rest % p.m_tiles, z = rest / p.m_tiles;
             const int as = it & 1;
             mbar_wait(&tmem_full_bar[as], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
@@ -268,6 +276,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v);
                 const int n0 = n_blk * BLOCK_N + c0;
+                if (p.splits > 1) {
+                    // split-K partial: fp32 RED into the workspace; bias / residual / conversion happen in k_splitk_finish
+                    if (row_ok) {
+                        float* wsp = p.splitk_ws + (size_t)m * p.N + n0;
+                        #pragma unroll
+                        for (int i = 0; i < 32; i++) atomicAdd(wsp + i, __uint_as_float(v[i]));
+                    }
+                    continue;
+                }
                 float f[32];
                 #pragma unroll
                 for (int i = 0; i < 32; i++) {
@@ -326,6 +343,29 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, C::kTmemCols); }
+}
+
+// split-K epilogue: out = alpha * ws + bias + row_bias (+ residual) -> fp16 ; 8 elements per thread
+static __global__ void k_splitk_finish(const float* __restrict__ ws, const GemmParams p) {
+    const size_t total = (size_t)p.m_valid * p.N / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e0 = i * 8; const int m = (int)(e0 / p.N), n0 = (int)(e0 % p.N);
+        const float4 a = *reinterpret_cast<const float4*>(ws + e0), b = *reinterpret_cast<const float4*>(ws + e0 + 4);
+        float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const float* rb = p.row_bias ? p.row_bias + (size_t)(m / p.rows_per_group) * p.N : nullptr;
+        #pragma unroll
+        for (int k = 0; k < 8; k++) { f[k] *= p.alpha; if (p.bias) f[k] += p.bias[n0 + k]; if (rb) f[k] += rb[n0 + k]; }
+        if (p.residual) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.ld_res + n0);
+            const __half* rh = reinterpret_cast<const __half*>(&rv);
+            #pragma unroll
+            for (int k = 0; k < 8; k++) f[k] += __half2float(rh[k]);
+        }
+        __align__(16) __half h[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) h[k] = __float2half_rn(f[k]);
+        *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldc + n0) = *reinterpret_cast<const uint4*>(h);
+    }
 }
 
 }  // namespace tc

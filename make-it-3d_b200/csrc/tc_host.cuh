@@ -57,6 +57,7 @@ inline int pick_block_n(int N, long long m_tiles_times_batch, int num_sms) {
     // largest tile that divides N; prefer 256 only when the grid still fills the machine
     if (N % 256 == 0 && m_tiles_times_batch * (N / 256) >= num_sms) return 256;
     if (N % 128 == 0 && m_tiles_times_batch * (N / 128) >= num_sms) return 128;
+    if (N % 160 == 0 && N % 128 != 0 && m_tiles_times_batch * (N / 160) >= num_sms / 2) return 160;   // N = 320: 2.5x the MACs per operand byte of BN = 64
     if (N % 64 == 0) return 64;
     return 0;
 }
@@ -69,7 +70,9 @@ inline int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmPar
         attr = true;
     }
     GemmParams q = p;
-    q.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M; q.n_tiles = p.N / BN; q.num_tiles = q.m_tiles * q.n_tiles * batch;
+    q.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M; q.n_tiles = p.N / BN;
+    if (q.splits <= 1) { q.splits = 1; q.kb_per_split = q.num_k_blocks; }
+    q.num_tiles = q.m_tiles * q.n_tiles * batch * q.splits;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const int resident = (Cfg<BN>::kSmemBytes <= 110 * 1024) ? 2 : 1;       // persistent grid: one (or two) CTAs per SM loop over the tiles
@@ -83,9 +86,32 @@ inline int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     switch (block_n) {
         case 64: return launch_bn<64>(ma, mb, p, batch, st);
         case 128: return launch_bn<128>(ma, mb, p, batch, st);
+        case 160: return launch_bn<160>(ma, mb, p, batch, st);
         case 256: return launch_bn<256>(ma, mb, p, batch, st);
     }
     return MI3D_ERR_ARG;
+}
+
+// Split-K for the deep U-Net / VAE levels (M = 128 .. 512 rows): a handful of output tiles with K = 3 000 .. 23 000 would otherwise
+// run on a handful of SMs.  ws: fp32 [M][N] scratch (zeroed here).  Only plain fp16-output GEMMs / convs with batch == 1.
+inline int plan_splits(long long tiles, int num_k_blocks, int num_sms) {
+    if (tiles * 2 > num_sms || num_k_blocks < 48) return 1;      // the zero-fill + finish passes cost ~10 us: only deep K pays
+    int s = (int)(num_sms / tiles);
+    if (s > 8) s = 8;
+    while (s > 1 && num_k_blocks / s < 8) s--;
+    return s;
+}
+inline int launch_splitk(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams p, int block_n, int splits, float* ws, cudaStream_t st) {
+    p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
+    p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;          // every K-range non-empty
+    p.splitk_ws = ws;
+    MI3D_CHECK(cudaMemsetAsync(ws, 0, (size_t)p.M * p.N * sizeof(float), st));
+    int r = launch(ma, mb, p, block_n, 1, st);
+    if (r) return r;
+    p.splits = 1;
+    const size_t total = (size_t)p.m_valid * p.N / 8;
+    k_splitk_finish<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, p);
+    return (int)cudaGetLastError();
 }
 
 }  // namespace tc

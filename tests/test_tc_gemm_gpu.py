@@ -40,6 +40,32 @@ def test_gemm_matches_fp32_reference(L, M, N, K, bn):
     assert (out16.float() - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K,bn,splits", [(128, 1280, 11520, 128, 8), (512, 1280, 5760, 128, 3), (256, 320, 2880, 160, 5),
+                                             (1024, 640, 1280, 64, 2)])
+def test_gemm_split_k(L, M, N, K, bn, splits):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).half()
+    ref = 0.5 * (a.float() @ b.float().t()) + bias + res.float()
+    out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    ws = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    L.check(L.lib().mi3d_gemm_f16_splitk(L.ptr(a), L.ptr(b), L.ptr(out), C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(bn), C.c_int(splits),
+                                         C.c_float(0.5), L.ptr(bias), L.ptr(res), L.ptr(ws), L.stream()), "gemm_f16_splitk")
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_block_n_160(L):
+    g = torch.Generator(device="cuda").manual_seed(160)
+    a = torch.randn(2048, 640, device="cuda", generator=g).half()
+    b = (torch.randn(320, 640, device="cuda", generator=g) / 640 ** 0.5).half()
+    ref = a.float() @ b.float().t()
+    out = _gemm(L, a, b, out_f32=True, block_n=160)
+    assert (out - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_gemm_epilogues(L):
     g = torch.Generator(device="cuda").manual_seed(5)
     M, N, K = 256, 256, 192
@@ -101,3 +127,26 @@ def test_gemm_mn_major_b_operand(L, M, N, K, bn):
     torch.cuda.synchronize()
     ref = a.float() @ bt.float()
     assert (out - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,T,Tk,valid,heads", [(2, 4096, 4096, 4096, 5), (2, 1024, 1024, 1024, 10), (2, 256, 128, 77, 20), (2, 64, 64, 64, 20),
+                                                (1, 16, 16, 16, 1), (1, 384, 300, 300, 2)])
+def test_flash_attention_matches_fp32_reference(L, B, T, Tk, valid, heads):
+    """Fused attention (S in TMEM, P through shared memory) vs torch fp32 softmax(q k^T / 8) v on the same fp16 inputs.
+    Bound: P is rounded to fp16 before the second product (2^-11 relative per term) + one fp16 rounding of the output."""
+    g = torch.Generator(device="cuda").manual_seed(B * T + heads)
+    C_ = heads * 64
+    q = torch.randn(B * T, C_, device="cuda", generator=g).half()
+    k = torch.randn(B * Tk, C_, device="cuda", generator=g).half()
+    v = torch.randn(B * Tk, C_, device="cuda", generator=g).half()
+    o = torch.zeros(B * T, C_, dtype=torch.float16, device="cuda")
+    L.check(L.lib().mi3d_flash_attn_f16(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), C.c_int(B), C.c_int(T), C.c_int(Tk), C.c_int(valid), C.c_int(heads),
+                                        C.c_int(C_), C.c_int(C_), C.c_int(C_), C.c_int(C_), L.stream()), "flash_attn")
+    torch.cuda.synchronize()
+    qf = q.float().view(B, T, heads, 64).permute(0, 2, 1, 3)
+    kf = k.float().view(B, Tk, heads, 64).permute(0, 2, 1, 3)[:, :, :valid]
+    vf = v.float().view(B, Tk, heads, 64).permute(0, 2, 1, 3)[:, :, :valid]
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) / 8.0, dim=-1) @ vf
+    ref = ref.permute(0, 2, 1, 3).reshape(B * T, C_)
+    err = (o.float() - ref).abs().max().item()
+    assert err < 3e-3 * max(1.0, ref.abs().max().item()), err

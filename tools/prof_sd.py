@@ -38,7 +38,26 @@ def main():
             te.append(e[0].elapsed_time(e[1])); tu.append(e[1].elapsed_time(e[2])); tb.append(e[2].elapsed_time(e[3]))
     med = lambda v: float(np.median(v))
     print(f"VAE encode fwd {med(te):.3f} ms | U-Net(x2)+CFG+SDS {med(tu):.3f} ms | VAE encode bwd {med(tb):.3f} ms | finite: {bool(torch.isfinite(rgb.grad).all())} {bool(torch.isfinite(npred).all())}")
+    if os.environ.get("MI3D_GEMM_DUMP"):
+        gemm_dump(g, rgb, ctx)
     print(f"tensor-roofline: unet {1.608e12 / (med(tu) * 1e-3) / 1e12:.1f} TFLOP/s, vae fwd {1.117e12 / (med(te) * 1e-3) / 1e12:.1f}, vae bwd {1.117e12 / (med(tb) * 1e-3) / 1e12:.1f}")
+
+
+def gemm_dump(g, rgb, ctx):
+    """Per-launch list of the tile kernel (CUDA events around each launch) for one guidance step -> gpurun_out/sd_gemms.txt"""
+    import ctypes as C
+    L = importlib.import_module("make-it-3d_b200._lib")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    os.environ["MI3D_SD_PROFILE_DUMP"] = os.path.join(ROOT, "gpurun_out", "sd_gemms.txt")
+    L.check(L.lib().mi3d_sd_profile(g.engine.h, C.c_int(1), None, None), "sd_profile")
+    rgb.grad = None
+    lat = g.encode_imgs(rgb)
+    npred, grad = g.unet_sds(lat, torch.randn_like(lat), g._t, ctx, 10.0)
+    lat.backward(gradient=grad)
+    torch.cuda.synchronize()
+    ms, n = C.c_float(0), C.c_int(0)
+    L.check(L.lib().mi3d_sd_profile(g.engine.h, C.c_int(0), C.byref(ms), C.byref(n)), "sd_profile")
+    print(f"tile kernel: {n.value} launches, {ms.value:.3f} ms")
 
 
 if __name__ == "__main__":
