@@ -145,7 +145,15 @@ typedef struct {
     uint32_t cap;              /* rows allocated in every per-sample buffer */
     const float* smooth_noise; /* [cap,3] N(0,1) (renderer.py:522) or NULL -> in-kernel Philox(seed,row) */
     uint64_t seed;
+    /* optional encoding cache shared by one forward and the backward(s) that follow it: fp32 [enc_cache_tiles][13][128][32]
+     * (mi3d_field_enc_cache_bytes).  mi3d_field_forward stores the hash-grid encodings of the first enc_cache_tiles 128-row tiles of
+     * every evaluation point there; mi3d_field_backward, when enc_cache_valid != 0, reads them back instead of re-gathering the
+     * table (same table, same samples: the caller vouches for it).  Rows beyond the cache are re-gathered.  NULL = off. */
+    float* enc_cache;
+    uint32_t enc_cache_tiles;
+    uint32_t enc_cache_valid;
 } mi3d_field_io;
+size_t mi3d_field_enc_cache_bytes(uint32_t tiles);
 
 /* number of CTAs the persistent field kernels launch; loss_partials must hold 2 * mi3d_field_grid_ctas(0) floats */
 int mi3d_field_grid_ctas(int backward);

@@ -37,7 +37,8 @@ class FieldCfg(C.Structure):
 
 class FieldIO(C.Structure):
     _fields_ = [("xyzs", C.c_void_p), ("dirs", C.c_void_p), ("counter", C.c_void_p), ("m_fixed", C.c_uint32),
-                ("align", C.c_uint32), ("cap", C.c_uint32), ("smooth_noise", C.c_void_p), ("seed", C.c_uint64)]
+                ("align", C.c_uint32), ("cap", C.c_uint32), ("smooth_noise", C.c_void_p), ("seed", C.c_uint64),
+                ("enc_cache", C.c_void_p), ("enc_cache_tiles", C.c_uint32), ("enc_cache_valid", C.c_uint32)]
 
 
 SHADING = {"albedo": 0, "lambertian": 1, "textureless": 2, "normal": 3}
@@ -49,7 +50,7 @@ SYMBOLS = [
     "mi3d_composite_rays_train_forward", "mi3d_composite_rays_train_backward",
     "mi3d_march_rays", "mi3d_composite_rays",
     "mi3d_hashgrid_make", "mi3d_hashgrid_forward", "mi3d_hashgrid_backward",
-    "mi3d_field_grid_ctas", "mi3d_field_forward", "mi3d_field_backward", "mi3d_field_backward_workspace_bytes",
+    "mi3d_field_grid_ctas", "mi3d_field_forward", "mi3d_field_backward", "mi3d_field_backward_workspace_bytes", "mi3d_field_enc_cache_bytes",
     "mi3d_density_grid_workspace_bytes", "mi3d_density_grid_update", "mi3d_version",
     "mi3d_gemm_f16", "mi3d_gemm_f16_splitk", "mi3d_flash_attn_f16", "mi3d_conv3x3_f16", "mi3d_tf32_tile_test", "mi3d_gemm_f16_bt",
     "mi3d_sd_workspace_bytes", "mi3d_sd_create", "mi3d_sd_destroy", "mi3d_sd_num_params", "mi3d_sd_param_name", "mi3d_sd_param_numel",
@@ -77,6 +78,7 @@ def lib():
         _lib.mi3d_march_rays_train_workspace_bytes.restype = C.c_size_t
         _lib.mi3d_density_grid_workspace_bytes.restype = C.c_size_t
         _lib.mi3d_field_backward_workspace_bytes.restype = C.c_size_t
+        _lib.mi3d_field_enc_cache_bytes.restype = C.c_size_t
         for name in ("mi3d_sd_workspace_bytes", "mi3d_sd_weight_bytes"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_size_t

@@ -436,6 +436,7 @@ struct FwdArgs {
     int n_evals, shading; float ratio; const float* light_d;
     const float* smooth_noise; uint64_t seed;
     float* sigmas; float* rgbs; float* normals; float* tape; float* loss_partials;
+    float* enc_cache; uint32_t enc_cache_tiles;     // optional: encodings of the first enc_cache_tiles tiles, laid out like the backward's enc_buf
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -789,6 +790,11 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
                 // gather first (registers), then wait for the A1 buffer to be released by the previous evaluation's layer-1 MMAs
                 float f[16];
                 gather16(a.table, lv, l0, lcount, u0, u1, u2, f);
+                if (a.enc_cache && tile < a.enc_cache_tiles) {        // keep the encodings for the backward pass (it would re-gather them)
+                    float4* dst = reinterpret_cast<float4*>(a.enc_cache + ((size_t)tile * 13 + e) * (T * 32) + (size_t)r * 32 + 16 * half);
+                    #pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                }
                 if (it > 0) tc::mbar_wait(a1_empty, (it - 1) & 1);
                 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -1721,6 +1727,7 @@ int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_h
     a.n_evals = cfg->n_evals; a.shading = cfg->shading; a.ratio = cfg->ambient_ratio; a.light_d = cfg->light_d;
     a.smooth_noise = io->smooth_noise; a.seed = io->seed;
     a.sigmas = sigmas; a.rgbs = rgbs; a.normals = normals; a.tape = tape; a.loss_partials = loss_partials;
+    a.enc_cache = (use_tc() && hg->n_levels == 16) ? io->enc_cache : nullptr; a.enc_cache_tiles = io->enc_cache_tiles;
     int grid = mi3d_field_grid_ctas(0);
     if (use_tc()) { grid = num_sms(); k_field_fwd_tc<<<grid, fwdtc::kThreads, fwdtc::kSmem, (cudaStream_t)stream>>>(a); }
     else k_field_fwd<<<grid, NT, smem_bytes(false), (cudaStream_t)stream>>>(a);
@@ -1750,11 +1757,14 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     if (use_tc_bwd()) {
         if (workspace && hg->n_levels == 16) {
             // split pipeline, chunk by chunk (the sample count lives on the device: chunks past it return immediately)
-            a.enc_buf = (float*)workspace; a.denc_buf = a.enc_buf + (size_t)kBwdChunkTiles * 13 * T * 32;
+            float* enc_tmp = (float*)workspace;
+            a.denc_buf = enc_tmp + (size_t)kBwdChunkTiles * 13 * T * 32;
+            const bool cached = io->enc_cache && io->enc_cache_valid && use_tc();
             const uint32_t total_tiles = (io->cap + T - 1) / T;
             for (uint32_t t0 = 0; t0 < total_tiles; t0 += kBwdChunkTiles) {
                 a.tile0 = t0; a.tile1 = t0 + kBwdChunkTiles;
-                k_bwd_enc_scatter<false><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a);
+                if (cached && (t0 + kBwdChunkTiles < total_tiles ? t0 + kBwdChunkTiles : total_tiles) <= io->enc_cache_tiles) a.enc_buf = io->enc_cache + (size_t)t0 * 13 * T * 32;   // saved by the forward
+                else { a.enc_buf = enc_tmp; k_bwd_enc_scatter<false><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a); }
                 k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
                 k_bwd_enc_scatter<true><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a);
                 if (!io->counter && (uint64_t)(t0 + kBwdChunkTiles) * T >= io->m_fixed) break;
@@ -1765,6 +1775,8 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     } else k_field_bwd<<<mi3d_field_grid_ctas(1), NT, smem_bytes(true), (cudaStream_t)stream>>>(a);
     MI3D_RETURN_LAUNCH();
 }
+
+size_t mi3d_field_enc_cache_bytes(uint32_t tiles) { return (size_t)tiles * 13 * T * 32 * sizeof(float); }
 
 size_t mi3d_density_grid_workspace_bytes(uint32_t C, uint32_t H) {
     const size_t n = (size_t)H * H * H;

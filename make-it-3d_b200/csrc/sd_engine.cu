@@ -296,24 +296,40 @@ struct Engine {
         // ---- self attention ----
         __half* ln = alloc16(M * C);
         layernorm(h, M, C, tb + ".norm1", ln);
-        __half* qb = alloc16(M * C); __half* kb = alloc16(M * C); __half* vb = alloc16(M * C);
-        linear(ln, M, C, (const __half*)param(tb + ".attn1.to_q.weight", {C, C}, PK_LINEAR).dst, C, qb);
-        linear(ln, M, C, (const __half*)param(tb + ".attn1.to_k.weight", {C, C}, PK_LINEAR).dst, C, kb);
-        linear(ln, M, C, (const __half*)param(tb + ".attn1.to_v.weight", {C, C}, PK_LINEAR).dst, C, vb);
+        // to_q / to_k / to_v weights are allocated back to back ([3C][C]): one GEMM produces q | k | v side by side
+        const __half* wq = (const __half*)param(tb + ".attn1.to_q.weight", {C, C}, PK_LINEAR).dst;
+        const __half* wk = (const __half*)param(tb + ".attn1.to_k.weight", {C, C}, PK_LINEAR).dst;
+        const __half* wv = (const __half*)param(tb + ".attn1.to_v.weight", {C, C}, PK_LINEAR).dst;
         __half* ao = alloc16(M * C);
-        attention_core(qb, C, kb, C, vb, C, B, T, T, T, heads, d, ao, C);
+        if (wk == wq + (size_t)C * C && wv == wk + (size_t)C * C) {
+            __half* qkv = alloc16(M * 3 * C);
+            linear(ln, M, C, wq, 3 * C, qkv);
+            attention_core(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, B, T, T, T, heads, d, ao, C);
+        } else {
+            __half* qb = alloc16(M * C); __half* kb = alloc16(M * C); __half* vb = alloc16(M * C);
+            linear(ln, M, C, wq, C, qb); linear(ln, M, C, wk, C, kb); linear(ln, M, C, wv, C, vb);
+            attention_core(qb, C, kb, C, vb, C, B, T, T, T, heads, d, ao, C);
+        }
         __half* h2 = alloc16(M * C);
         linear(ao, M, C, (const __half*)param(tb + ".attn1.to_out.0.weight", {C, C}, PK_LINEAR).dst, C, h2, pf(tb + ".attn1.to_out.0.bias", {C}), h);
         // ---- cross attention (keys/values from the text context, padded to ctx_pad rows per batch) ----
         __half* ln2 = alloc16(M * C);
         layernorm(h2, M, C, tb + ".norm2", ln2);
         const long long Mc = (long long)B * ctx_pad;
-        __half* q2 = alloc16(M * C); __half* k2 = alloc16(Mc * C); __half* v2 = alloc16(Mc * C);
+        __half* q2 = alloc16(M * C);
         linear(ln2, M, C, (const __half*)param(tb + ".attn2.to_q.weight", {C, C}, PK_LINEAR).dst, C, q2);
-        linear(ctx16, Mc, cross, (const __half*)param(tb + ".attn2.to_k.weight", {C, cross}, PK_LINEAR).dst, C, k2);
-        linear(ctx16, Mc, cross, (const __half*)param(tb + ".attn2.to_v.weight", {C, cross}, PK_LINEAR).dst, C, v2);
+        const __half* wk2 = (const __half*)param(tb + ".attn2.to_k.weight", {C, cross}, PK_LINEAR).dst;
+        const __half* wv2 = (const __half*)param(tb + ".attn2.to_v.weight", {C, cross}, PK_LINEAR).dst;
         __half* ao2 = alloc16(M * C);
-        attention_core(q2, C, k2, C, v2, C, B, T, ctx_pad, ucfg.ctx_len, heads, d, ao2, C);
+        if (wv2 == wk2 + (size_t)C * cross) {
+            __half* kv = alloc16(Mc * 2 * C);
+            linear(ctx16, Mc, cross, wk2, 2 * C, kv);
+            attention_core(q2, C, kv, 2 * C, kv + C, 2 * C, B, T, ctx_pad, ucfg.ctx_len, heads, d, ao2, C);
+        } else {
+            __half* k2 = alloc16(Mc * C); __half* v2 = alloc16(Mc * C);
+            linear(ctx16, Mc, cross, wk2, C, k2); linear(ctx16, Mc, cross, wv2, C, v2);
+            attention_core(q2, C, k2, C, v2, C, B, T, ctx_pad, ucfg.ctx_len, heads, d, ao2, C);
+        }
         __half* h3 = alloc16(M * C);
         linear(ao2, M, C, (const __half*)param(tb + ".attn2.to_out.0.weight", {C, C}, PK_LINEAR).dst, C, h3, pf(tb + ".attn2.to_out.0.bias", {C}), h2);
         // ---- GEGLU feed-forward ----
