@@ -1382,7 +1382,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         // column sums for db2 / db1: this thread sums column cj over rows [rs, rs + 32)
         const int cj = et & 63, rs = (et >> 6) * 32;
-        const bool ext = a.enc_buf != nullptr;
+        const bool ext = a.enc_buf != nullptr, ext_out = a.denc_buf != nullptr;
         float ab2 = 0.f, ab1 = 0.f;
         for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
@@ -1468,7 +1468,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 tc::tc_fence_before();
                 // chain(e) has retired: E is free -> hand the next evaluation to the MMA warp before scattering this one
                 if (e + 1 < e_end) write_E(f);
-                if (ext) {
+                if (ext_out) {
                     float4* dst = reinterpret_cast<float4*>(a.denc_buf + ((size_t)(tile - a.tile0) * 13 + e) * (T * 32) + (size_t)r * 32 + 16 * half);
                     #pragma unroll
                     for (int q = 0; q < 4; q++) dst[q] = make_float4(__uint_as_float(g[4 * q]), __uint_as_float(g[4 * q + 1]), __uint_as_float(g[4 * q + 2]), __uint_as_float(g[4 * q + 3]));
@@ -1763,8 +1763,20 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
             const uint32_t total_tiles = (io->cap + T - 1) / T;
             for (uint32_t t0 = 0; t0 < total_tiles; t0 += kBwdChunkTiles) {
                 a.tile0 = t0; a.tile1 = t0 + kBwdChunkTiles;
-                if (cached && (t0 + kBwdChunkTiles < total_tiles ? t0 + kBwdChunkTiles : total_tiles) <= io->enc_cache_tiles) a.enc_buf = io->enc_cache + (size_t)t0 * 13 * T * 32;   // saved by the forward
-                else { a.enc_buf = enc_tmp; k_bwd_enc_scatter<false><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a); }
+                float* const denc = a.denc_buf;
+                bool fused_scatter = false;
+                if (cached && (t0 + kBwdChunkTiles < total_tiles ? t0 + kBwdChunkTiles : total_tiles) <= io->enc_cache_tiles) {
+                    a.enc_buf = io->enc_cache + (size_t)t0 * 13 * T * 32;   // saved by the forward
+                    static int fs = -1; if (fs < 0) { const char* e = getenv("MI3D_BWD_FUSED_SCATTER"); fs = (e && e[0] == '1') ? 1 : 0; }
+                    fused_scatter = fs == 1;
+                } else { a.enc_buf = enc_tmp; k_bwd_enc_scatter<false><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a); }
+                if (fused_scatter) {      // no gather left to hide: the chain kernel's encoder warps scatter d(enc) themselves
+                    a.denc_buf = nullptr;
+                    k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
+                    a.denc_buf = denc;
+                    if (!io->counter && (uint64_t)(t0 + kBwdChunkTiles) * T >= io->m_fixed) break;
+                    continue;
+                }
                 k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
                 k_bwd_enc_scatter<true><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a);
                 if (!io->counter && (uint64_t)(t0 + kBwdChunkTiles) * T >= io->m_fixed) break;

@@ -50,6 +50,20 @@ struct Engine {
     std::vector<Param> params; std::map<std::string, int> pindex;
     std::vector<Op> unet_ops, enc_ops, enc_bwd_ops;
     std::vector<Op>* cur = nullptr;
+    // GroupNorm statistics of one op list live in one pool, cleared by a single memset at the head of the list
+    uint8_t* pool = nullptr; size_t pool_used = 0; static constexpr size_t kPoolBytes = 256 * 1024;
+    void begin_list(std::vector<Op>* l) {
+        cur = l; pool = (uint8_t*)alloc(kPoolBytes); pool_used = 0;
+        uint8_t* pp = pool;
+        push([pp](cudaStream_t st) { return (int)cudaMemsetAsync(pp, 0, kPoolBytes, st); });
+    }
+    double* pool_stats(size_t n_doubles) {
+        const size_t b = n_doubles * sizeof(double);
+        if (pool_used + b > kPoolBytes) { err = MI3D_ERR_ARG; return (double*)pool; }
+        double* p = (double*)(pool + pool_used); pool_used += b; return p;
+    }
+    // per-ResBlock time-embedding projections of the whole U-Net, evaluated by one grouped launch right after the embedding MLP
+    std::vector<sdk::SmallLinearJob> temb_jobs; sdk::SmallLinearJob* temb_jobs_dev = nullptr; int temb_max_n = 0;
     std::map<std::string, std::pair<void*, size_t>> named;   // debug taps: name -> (ptr, bytes)
     // fixed I/O buffers
     T4 unet_in; float* unet_out = nullptr; __half* ctx16 = nullptr; float* temb = nullptr; long long* t_dev = nullptr;
@@ -177,7 +191,7 @@ struct Engine {
     GN groupnorm(const T4& x, const std::string& pname, float eps, int silu, const T4& y) {
         GN g; g.x = x; g.G = ucfg.groups; g.eps = eps; g.silu = silu;
         g.gamma = pf(pname + ".weight", {x.c}); g.beta = pf(pname + ".bias", {x.c});
-        g.stats = (double*)alloc((size_t)x.n * g.G * 2 * sizeof(double));
+        g.stats = pool_stats((size_t)x.n * g.G * 2);
         if (dry) return g;
         const int HW = x.h * x.w, C = x.c, G = g.G, N = x.n;
         const int VPP = C / 8, PL = std::max(1, 256 / VPP), threads = PL * VPP;
@@ -187,7 +201,6 @@ struct Engine {
         const int ppc = (HW + chunks - 1) / chunks; chunks = (HW + ppc - 1) / ppc;
         const __half* xp = x.p; __half* yp = y.p; const GN gg = g;
         push([=](cudaStream_t st) {
-            cudaMemsetAsync(gg.stats, 0, (size_t)N * G * 2 * sizeof(double), st);
             sdk::k_gn_stats<<<dim3(chunks, N), threads, 2 * C * sizeof(float), st>>>(xp, HW, C, G, ppc, gg.stats);
             sdk::k_gn_apply<<<dim3(chunks, N), threads, 0, st>>>(xp, yp, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, ppc);
             return (int)cudaGetLastError();
@@ -196,7 +209,7 @@ struct Engine {
     }
     // dx = GN(+SiLU) backward of dy (+ add)
     void groupnorm_bwd(const GN& g, const __half* dy, const __half* add, __half* dx) {
-        double* bstats = (double*)alloc((size_t)g.x.n * g.G * 2 * sizeof(double));
+        double* bstats = pool_stats((size_t)g.x.n * g.G * 2);
         if (dry) return;
         const int HW = g.x.h * g.x.w, C = g.x.c, G = g.G, N = g.x.n;
         const int VPP = C / 8, PL = std::max(1, 256 / VPP), threads = PL * VPP;
@@ -204,7 +217,6 @@ struct Engine {
         const int ppc = (HW + chunks - 1) / chunks; chunks = (HW + ppc - 1) / ppc;
         const GN gg = g;
         push([=](cudaStream_t st) {
-            cudaMemsetAsync(bstats, 0, (size_t)N * G * 2 * sizeof(double), st);
             sdk::k_gn_bwd_stats<<<dim3(chunks, N), threads, 2 * C * sizeof(float), st>>>(gg.x.p, dy, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, ppc, bstats);
             sdk::k_gn_bwd_apply<<<dim3(chunks, N), threads, 0, st>>>(gg.x.p, dy, gg.stats, bstats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, add, dx, ppc);
             return (int)cudaGetLastError();
@@ -236,6 +248,9 @@ struct Engine {
         });
     }
     static int blocks_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
+    // persistent grids of the small direct convolutions: as many CTAs per SM as their weight staging area allows
+    int small_cin_grid(size_t outputs, size_t smem) const { const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1))); return (int)std::min<size_t>((outputs / 8 + 255) / 256, (size_t)num_sms * per_sm); }
+    int small_cout_grid(size_t pixels, int cin) const { const int ppw = cin <= 128 ? 2 : 1; return (int)std::min<size_t>((pixels / ppw + 7) / 8 + 1, (size_t)num_sms * 8); }
 
     // ------------------------------------------------------------------------------------------------------
     // U-Net pieces (diffusers naming)
@@ -250,7 +265,8 @@ struct Engine {
             const __half* wt = (const __half*)param(pre + ".time_emb_proj.weight", {cout, tdim}, PK_LINEAR).dst;
             const float* bt = pf(pre + ".time_emb_proj.bias", {cout});
             float* tp = alloc32((size_t)x.n * cout);
-            linear_small(temb, wt, bt, tp, x.n, cout, tdim, 1, 0);
+            temb_jobs.push_back({wt, bt, tp, cout});          // evaluated by the grouped launch at the head of the U-Net
+            temb_max_n = std::max(temb_max_n, cout);
             rb = tp;
         }
         const bool both = tape != nullptr;
@@ -374,7 +390,7 @@ struct Engine {
     }
 
     void build_unet() {
-        cur = &unet_ops;
+        begin_list(&unet_ops);
         const mi3d_unet_cfg& c = ucfg;
         const int B = c.batch, HW = c.latent_hw, nlev = c.n_levels, L = c.layers_per_block;
         const int c0 = c.block_out[0], tdim = c0 * 4;
@@ -393,6 +409,14 @@ struct Engine {
             });
             linear_small(tproj, (const __half*)param("time_embedding.linear_1.weight", {tdim, c0}, PK_LINEAR).dst, pf("time_embedding.linear_1.bias", {tdim}), t1, B, tdim, c0, 0, 1);
             linear_small(t1, (const __half*)param("time_embedding.linear_2.weight", {tdim, tdim}, PK_LINEAR).dst, pf("time_embedding.linear_2.bias", {tdim}), temb, B, tdim, tdim, 0, 0);
+            temb_jobs.clear(); temb_max_n = 0;
+            temb_jobs_dev = (sdk::SmallLinearJob*)alloc(64 * sizeof(sdk::SmallLinearJob));
+            const float* te = temb;
+            push([this, te, B, tdim](cudaStream_t st) {
+                if (temb_jobs.empty()) return 0;
+                sdk::k_linear_small_grouped<<<dim3((temb_max_n + 7) / 8, (unsigned)temb_jobs.size()), 256, 0, st>>>(te, temb_jobs_dev, B, tdim);
+                return (int)cudaGetLastError();
+            });
         }
         // conv_in (Cin = 4): direct
         T4 h = act(B, HW, HW, c0);
@@ -401,8 +425,9 @@ struct Engine {
             const float* b = pf("conv_in.bias", {c0});
             const T4 xin = unet_in, ho = h; const int cin = c.in_ch;
             push([=](cudaStream_t st) {
-                if (cin != 4) return (int)MI3D_ERR_ARG;
-                sdk::k_conv_small_cin<4><<<blocks_for(ho.numel()), 256, (size_t)c0 * 9 * 4 * sizeof(float), st>>>(xin.p, w, b, ho.p, xin.n, xin.h, xin.w, c0);
+                if (cin != 4 || c0 % 8) return (int)MI3D_ERR_ARG;
+                const size_t sm = (size_t)c0 * 9 * 4 * sizeof(float);
+                sdk::k_conv_small_cin<4><<<small_cin_grid(ho.numel(), sm), 256, sm, st>>>(xin.p, w, b, ho.p, xin.n, xin.h, xin.w, c0);
                 return (int)cudaGetLastError();
             });
         }
@@ -459,10 +484,13 @@ struct Engine {
             push([=](cudaStream_t st) {
                 if (oc != 4) return (int)MI3D_ERR_ARG;
                 const size_t pix = (size_t)a.rows();
-                sdk::k_conv_small_cout<4><<<(unsigned)((pix + 7) / 8), 256, 0, st>>>(a.p, w, b, o, a.n, a.h, a.w, a.c);
+                sdk::k_conv_small_cout<4><<<small_cout_grid(pix, a.c), 256, (size_t)4 * 9 * a.c * 2, st>>>(a.p, w, b, o, a.n, a.h, a.w, a.c);
                 return (int)cudaGetLastError();
             });
         }
+        if (temb_jobs.size() > 64) err = MI3D_ERR_ARG;
+        if (!dry && !err && !temb_jobs.empty())
+            if (cudaMemcpy(temb_jobs_dev, temb_jobs.data(), temb_jobs.size() * sizeof(sdk::SmallLinearJob), cudaMemcpyHostToDevice) != cudaSuccess) err = MI3D_ERR_ARG;
         cur = nullptr;
     }
 
@@ -503,7 +531,7 @@ struct Engine {
     }
 
     void build_vae() {
-        cur = &enc_ops;
+        begin_list(&enc_ops);
         const mi3d_vae_cfg& c = vcfg;
         const int S = c.image_hw, nlev = c.n_levels, L = c.layers_per_block;
         vae_in = act(1, S, S, 4);          // 3 channels padded to 4 (the 4th is zero)
@@ -513,7 +541,9 @@ struct Engine {
             const float* b = pf("encoder.conv_in.bias", {c.block_out[0]});
             const T4 xin = vae_in, ho = h; const int co = c.block_out[0];
             push([=](cudaStream_t st) {
-                sdk::k_conv_small_cin<4><<<blocks_for(ho.numel()), 256, (size_t)co * 9 * 4 * sizeof(float), st>>>(xin.p, w, b, ho.p, 1, xin.h, xin.w, co);
+                if (co % 8) return (int)MI3D_ERR_ARG;
+                const size_t sm = (size_t)co * 9 * 4 * sizeof(float);
+                sdk::k_conv_small_cin<4><<<small_cin_grid(ho.numel(), sm), 256, sm, st>>>(xin.p, w, b, ho.p, 1, xin.h, xin.w, co);
                 return (int)cudaGetLastError();
             });
         }
@@ -572,7 +602,7 @@ struct Engine {
             const T4 a = v_a_out;
             push([=](cudaStream_t st) {
                 if (l2 != 8) return (int)MI3D_ERR_ARG;
-                sdk::k_conv_small_cout<8><<<(unsigned)((a.rows() + 7) / 8), 256, 0, st>>>(a.p, w, b, co, a.n, a.h, a.w, a.c);
+                sdk::k_conv_small_cout<8><<<small_cout_grid((size_t)a.rows(), a.c), 256, (size_t)8 * 9 * a.c * 2, st>>>(a.p, w, b, co, a.n, a.h, a.w, a.c);
                 return (int)cudaGetLastError();
             });
         }
@@ -588,7 +618,7 @@ struct Engine {
     }
 
     void build_vae_bwd() {
-        cur = &enc_bwd_ops;
+        begin_list(&enc_bwd_ops);
         const mi3d_vae_cfg& c = vcfg;
         const int l2 = 2 * c.latent_ch;
         const T4 hl = v_h_last; const int ch = hl.c;
@@ -602,7 +632,9 @@ struct Engine {
             push([=](cudaStream_t st) {
                 // fp32 -> fp16 staging of the 8-channel gradient
                 sdk::k_f32_to_f16<<<blocks_for(g8c.numel()), 256, 0, st>>>(gm, g8c.p, g8c.numel());
-                sdk::k_conv_small_cin<8><<<blocks_for(dac.numel()), 256, (size_t)ch * 9 * 8 * sizeof(float), st>>>(g8c.p, wf, nullptr, dac.p, g8c.n, g8c.h, g8c.w, ch);
+                if (ch % 8) return (int)MI3D_ERR_ARG;
+                const size_t sm = (size_t)ch * 9 * 8 * sizeof(float);
+                sdk::k_conv_small_cin<8><<<small_cin_grid(dac.numel(), sm), 256, sm, st>>>(g8c.p, wf, nullptr, dac.p, g8c.n, g8c.h, g8c.w, ch);
                 return (int)cudaGetLastError();
             });
         }
@@ -686,7 +718,7 @@ struct Engine {
             const __half* w = (const __half*)param("encoder.conv_in.weight#dgrad", {4, c.block_out[0], 3, 3}, PK_CONV_SMALL_COUT).dst;
             const T4 d = dh;
             push([=](cudaStream_t st) {
-                sdk::k_conv_small_cout<4><<<(unsigned)((d.rows() + 7) / 8), 256, 0, st>>>(d.p, w, nullptr, gimg, d.n, d.h, d.w, d.c);
+                sdk::k_conv_small_cout<4><<<small_cout_grid((size_t)d.rows(), d.c), 256, (size_t)4 * 9 * d.c * 2, st>>>(d.p, w, nullptr, gimg, d.n, d.h, d.w, d.c);
                 return (int)cudaGetLastError();
             });
         }
@@ -854,6 +886,8 @@ mi3d_sd_t mi3d_sd_create(const mi3d_unet_cfg* u, const mi3d_vae_cfg* v, void* wo
     if (h->e.build(false) != 0) { delete h; return nullptr; }
     cudaFuncSetAttribute(sdk::k_conv_small_cin<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(sdk::k_conv_small_cin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(sdk::k_conv_small_cout<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(sdk::k_conv_small_cout<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     return h;
 }
 

@@ -401,18 +401,26 @@ __global__ void k_add(const __half* __restrict__ a, const __half* __restrict__ b
 // small direct 3x3 convolutions (stride 1, pad 1), NHWC.  Used where the channel count is too small for the
 // 64-wide K blocks of the tensor-core tiles: conv_in (Cin = 3 / 4), conv_out (Cout = 4 / 8) and their transposes.
 // ------------------------------------------------------------------------------------------------------------
-// small Cin (<= 8): thread per (pixel, cout); in fp16 [N,H,W,Cin], w fp32 [Cout][3][3][Cin] in shared, out fp16 [N,H,W,Cout]
+// small Cin (<= 8): thread per (pixel, 8 output channels); in fp16 [N,H,W,CIN], w fp32 [Cout][3][3][CIN] (transposed into shared
+// memory as [tap][cin][Cout] so the 8 channels of a thread are two conflict-free float4 reads), out fp16 [N,H,W,Cout].
+// Persistent grid (a few CTAs per SM): the weight staging is paid once per CTA, the 27/72 inputs once per 8 outputs.  Cout % 8 == 0.
 template <int CIN>
 __global__ void k_conv_small_cin(const __half* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ out,
                                  int N, int H, int W, int Cout) {
-    extern __shared__ float sw[];                 // [Cout][9*CIN]
-    for (int i = threadIdx.x; i < Cout * 9 * CIN; i += blockDim.x) sw[i] = w[i];
+    extern __shared__ float sw[];                 // [9*CIN][Cout]
+    for (int i = threadIdx.x; i < Cout * 9 * CIN; i += blockDim.x) {
+        const int co = i / (9 * CIN), r = i % (9 * CIN);
+        sw[r * Cout + co] = w[i];
+    }
     __syncthreads();
-    const size_t total = (size_t)N * H * W * Cout;
+    const int CG = Cout / 8;
+    const size_t total = (size_t)N * H * W * CG;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int co = (int)(i % Cout); size_t p = i / Cout;
-        const int x = (int)(p % W); p /= W; const int y = (int)(p % H); const int n = (int)(p / H);
-        float acc = bias ? bias[co] : 0.f;
+        const int cg = (int)(i % CG); size_t p = i / CG;
+        const int x = (int)(p % W); const size_t q = p / W; const int y = (int)(q % H); const int n = (int)(q / H);
+        float acc[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = bias ? bias[cg * 8 + k] : 0.f;
         #pragma unroll
         for (int ky = 0; ky < 3; ky++) {
             const int yy = y + ky - 1; if (yy < 0 || yy >= H) continue;
@@ -420,48 +428,83 @@ __global__ void k_conv_small_cin(const __half* __restrict__ in, const float* __r
             for (int kx = 0; kx < 3; kx++) {
                 const int xx = x + kx - 1; if (xx < 0 || xx >= W) continue;
                 const __half* ip = in + (((size_t)n * H + yy) * W + xx) * CIN;
-                const float* wp = sw + (co * 9 + ky * 3 + kx) * CIN;
-                #pragma unroll
-                for (int c = 0; c < CIN; c++) acc = fmaf(__half2float(ip[c]), wp[c], acc);
-            }
-        }
-        out[i] = __float2half_rn(acc);
-    }
-}
-// small Cout (<= 8): warp per pixel, lanes split Cin (8 channels per lane step); w fp16 [Cout][3][3][Cin]; out fp32 [N,H,W,Cout]
-template <int COUT>
-__global__ void k_conv_small_cout(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                                  int N, int H, int W, int Cin) {
-    const size_t pix = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (pix >= (size_t)N * H * W) return;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
-    float acc[COUT];
-    #pragma unroll
-    for (int o = 0; o < COUT; o++) acc[o] = 0.f;
-    for (int ky = 0; ky < 3; ky++) {
-        const int yy = y + ky - 1; if (yy < 0 || yy >= H) continue;
-        for (int kx = 0; kx < 3; kx++) {
-            const int xx = x + kx - 1; if (xx < 0 || xx >= W) continue;
-            const __half* ip = in + (((size_t)n * H + yy) * W + xx) * Cin;
-            for (int c = lane * 8; c < Cin; c += 256) {
-                const uint4 ri = *reinterpret_cast<const uint4*>(ip + c);
-                const __half* hi = reinterpret_cast<const __half*>(&ri);
-                #pragma unroll
-                for (int o = 0; o < COUT; o++) {
-                    const uint4 rw = *reinterpret_cast<const uint4*>(w + ((size_t)(o * 9 + ky * 3 + kx)) * Cin + c);
-                    const __half* hw = reinterpret_cast<const __half*>(&rw);
+                float v[CIN];
+                if (CIN == 8) {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ip));
+                    const __half* h = reinterpret_cast<const __half*>(&raw);
                     #pragma unroll
-                    for (int k = 0; k < 8; k++) acc[o] = fmaf(__half2float(hi[k]), __half2float(hw[k]), acc[o]);
+                    for (int c = 0; c < CIN; c++) v[c] = __half2float(h[c]);
+                } else {
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(ip));
+                    const __half* h = reinterpret_cast<const __half*>(&raw);
+                    #pragma unroll
+                    for (int c = 0; c < CIN; c++) v[c] = __half2float(h[c]);
+                }
+                const float* wp = sw + (size_t)((ky * 3 + kx) * CIN) * Cout + cg * 8;
+                #pragma unroll
+                for (int c = 0; c < CIN; c++) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wp + (size_t)c * Cout), w1 = *reinterpret_cast<const float4*>(wp + (size_t)c * Cout + 4);
+                    acc[0] = fmaf(v[c], w0.x, acc[0]); acc[1] = fmaf(v[c], w0.y, acc[1]); acc[2] = fmaf(v[c], w0.z, acc[2]); acc[3] = fmaf(v[c], w0.w, acc[3]);
+                    acc[4] = fmaf(v[c], w1.x, acc[4]); acc[5] = fmaf(v[c], w1.y, acc[5]); acc[6] = fmaf(v[c], w1.z, acc[6]); acc[7] = fmaf(v[c], w1.w, acc[7]);
                 }
             }
         }
-    }
-    #pragma unroll
-    for (int o = 0; o < COUT; o++) { acc[o] = warp_sum(acc[o]); }
-    if (lane == 0) {
+        __align__(16) __half o[8];
         #pragma unroll
-        for (int o = 0; o < COUT; o++) out[pix * COUT + o] = acc[o] + (bias ? bias[o] : 0.f);
+        for (int k = 0; k < 8; k++) o[k] = __float2half_rn(acc[k]);
+        *reinterpret_cast<uint4*>(out + p * Cout + cg * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+// small Cout (<= 8): a group of LPP lanes per pixel (16 when Cin <= 128, else 32) splits Cin in 8-channel vectors; the fp16 weights
+// [Cout][3][3][Cin] are staged in shared memory once per CTA; persistent grid-stride loop over pixels; out fp32 [N,H,W,Cout]
+template <int COUT>
+__global__ void k_conv_small_cout(const __half* __restrict__ in, const __half* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                                  int N, int H, int W, int Cin) {
+    extern __shared__ __half swh[];               // [COUT][9][Cin]
+    for (int i = threadIdx.x; i < COUT * 9 * Cin / 8; i += blockDim.x) reinterpret_cast<uint4*>(swh)[i] = __ldg(reinterpret_cast<const uint4*>(w) + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int LPP = Cin <= 128 ? 16 : 32, sub = lane / LPP, sl = lane % LPP, ppw = 32 / LPP;
+    const size_t npix = (size_t)N * H * W;
+    const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5), wid = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (size_t base = wid * ppw; base < npix; base += warps * ppw) {
+        const size_t pix = base + sub;
+        const bool live = pix < npix;
+        const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+        float acc[COUT];
+        #pragma unroll
+        for (int o = 0; o < COUT; o++) acc[o] = 0.f;
+        if (live)
+        for (int ky = 0; ky < 3; ky++) {
+            const int yy = y + ky - 1; if (yy < 0 || yy >= H) continue;
+            for (int kx = 0; kx < 3; kx++) {
+                const int xx = x + kx - 1; if (xx < 0 || xx >= W) continue;
+                const __half* ip = in + (((size_t)n * H + yy) * W + xx) * Cin;
+                for (int c = sl * 8; c < Cin; c += LPP * 8) {
+                    const uint4 ri = __ldg(reinterpret_cast<const uint4*>(ip + c));
+                    const __half2* hi = reinterpret_cast<const __half2*>(&ri);
+                    float2 f[4];
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) f[k] = __half22float2(hi[k]);
+                    #pragma unroll
+                    for (int o = 0; o < COUT; o++) {
+                        const uint4 rw = *reinterpret_cast<const uint4*>(swh + ((size_t)(o * 9 + ky * 3 + kx)) * Cin + c);
+                        const __half2* hw = reinterpret_cast<const __half2*>(&rw);
+                        #pragma unroll
+                        for (int k = 0; k < 4; k++) { const float2 g = __half22float2(hw[k]); acc[o] = fmaf(f[k].x, g.x, fmaf(f[k].y, g.y, acc[o])); }
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int o = 0; o < COUT; o++) {
+            #pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) if (m < LPP) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
+        }
+        if (live && sl == 0) {
+            #pragma unroll
+            for (int o = 0; o < COUT; o++) out[pix * COUT + o] = acc[o] + (bias ? bias[o] : 0.f);
+        }
     }
 }
 
@@ -482,6 +525,27 @@ __global__ void k_linear_small(const float* __restrict__ x, const __half* __rest
     for (int b = 0; b < B; b++) {
         float v = warp_sum(acc[b]);
         if (lane == 0) { v += bias ? bias[n] : 0.f; if (silu_out) v = silu(v); y[(size_t)b * N + n] = v; }
+    }
+}
+
+// the same for a table of layers sharing the input x (SiLU applied to x): blockIdx.y = layer
+struct SmallLinearJob { const __half* w; const float* bias; float* y; int N; };
+__global__ void k_linear_small_grouped(const float* __restrict__ x, const SmallLinearJob* __restrict__ jobs, int B, int K) {
+    const SmallLinearJob jb = jobs[blockIdx.y];
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= jb.N) return;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane * 8; k < K; k += 256) {
+        const uint4 rw = *reinterpret_cast<const uint4*>(jb.w + (size_t)n * K + k);
+        const __half* hw = reinterpret_cast<const __half*>(&rw);
+        for (int b = 0; b < B; b++) {
+            #pragma unroll
+            for (int j = 0; j < 8; j++) acc[b] = fmaf(silu(x[(size_t)b * K + k + j]), __half2float(hw[j]), acc[b]);
+        }
+    }
+    for (int b = 0; b < B; b++) {
+        const float v = warp_sum(acc[b]);
+        if (lane == 0) jb.y[(size_t)b * jb.N + n] = v + (jb.bias ? jb.bias[n] : 0.f);
     }
 }
 
