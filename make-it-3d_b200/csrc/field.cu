@@ -123,30 +123,48 @@ __device__ __forceinline__ void scatter_level_agg(float* __restrict__ gtable, co
                                                   float g0, float g1, bool active, bool aggregate, int lane) {
     const CellW cw = hg_cell(u0, u1, u2, L.scale);
     float2* __restrict__ base = reinterpret_cast<float2*>(gtable) + L.offset;
+    // runs = maximal stretches of ADJACENT active lanes in the same cell: all eight corner keys of such lanes coincide, so the run
+    // structure (segment ids + the five scan predicates) is computed once per level and shared by the 16 scanned values
+    uint32_t heads = 0xffffffffu, takem = 0u;
+    if (aggregate) {
+        const uint32_t c0 = active ? cw.c[0] : 0xFFFFFF00u + (uint32_t)lane, c1 = cw.c[1], c2 = cw.c[2];
+        const uint32_t p0 = __shfl_up_sync(0xffffffffu, c0, 1), p1 = __shfl_up_sync(0xffffffffu, c1, 1), p2 = __shfl_up_sync(0xffffffffu, c2, 1);
+        heads = __ballot_sync(0xffffffffu, lane == 0 || p0 != c0 || p1 != c1 || p2 != c2);
+        const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
+        #pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const int su = __shfl_up_sync(0xffffffffu, seg, 1 << i);
+            if (lane >= (1 << i) && su == seg) takem |= 1u << i;
+        }
+    }
+    const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    const bool issue = active && (!aggregate || tail);
+    // the two x-neighbours of a (cy, cz) corner pair are adjacent table entries whenever idx(x+1) == idx(x) ^ 1 (dense levels with an
+    // even index; hashed power-of-two levels with an even cell x, where the +1 only flips bit 0 of the xor-hash): one 16-byte RED
+    // then carries both.  RED rate, not issue slots, bounds this kernel (measured), so fewer, wider REDs are the lever.
     #pragma unroll
-    for (int corner = 0; corner < 8; corner++) {
-        const uint32_t cx = cw.c[0] + (corner & 1), cy = cw.c[1] + ((corner >> 1) & 1), cz = cw.c[2] + ((corner >> 2) & 1);
-        const float wx = (corner & 1) ? cw.w[0] : 1 - cw.w[0];
-        const float wy = (corner & 2) ? cw.w[1] : 1 - cw.w[1];
-        const float wz = (corner & 4) ? cw.w[2] : 1 - cw.w[2];
-        const float wt = wx * wy * wz;
-        uint32_t key = active ? hg_index(cx, cy, cz, L) : (0xFFFFFF00u + (uint32_t)lane);
-        float v0 = active ? wt * g0 : 0.f, v1 = active ? wt * g1 : 0.f;
+    for (int yz = 0; yz < 4; yz++) {
+        const uint32_t cy = cw.c[1] + (yz & 1), cz = cw.c[2] + (yz >> 1);
+        const float wyz = ((yz & 1) ? cw.w[1] : 1 - cw.w[1]) * ((yz & 2) ? cw.w[2] : 1 - cw.w[2]);
+        const float wt0 = (1 - cw.w[0]) * wyz, wt1 = cw.w[0] * wyz;
+        float v00 = active ? wt0 * g0 : 0.f, v01 = active ? wt0 * g1 : 0.f, v10 = active ? wt1 * g0 : 0.f, v11 = active ? wt1 * g1 : 0.f;
         if (aggregate) {
-            // runs = maximal stretches of ADJACENT lanes with the same key (equal keys further apart stay separate runs)
-            const uint32_t kp = __shfl_up_sync(0xffffffffu, key, 1);
-            const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || kp != key);
-            const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
             #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int su = __shfl_up_sync(0xffffffffu, seg, d);
-                const float a0 = __shfl_up_sync(0xffffffffu, v0, d), a1 = __shfl_up_sync(0xffffffffu, v1, d);
-                if (lane >= d && su == seg) { v0 += a0; v1 += a1; }
+            for (int i = 0; i < 5; i++) {
+                const float a00 = __shfl_up_sync(0xffffffffu, v00, 1 << i), a01 = __shfl_up_sync(0xffffffffu, v01, 1 << i);
+                const float a10 = __shfl_up_sync(0xffffffffu, v10, 1 << i), a11 = __shfl_up_sync(0xffffffffu, v11, 1 << i);
+                if ((takem >> i) & 1u) { v00 += a00; v01 += a01; v10 += a10; v11 += a11; }
             }
-            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-            if (active && tail && (v0 != 0.f || v1 != 0.f)) atomicAdd(base + key, make_float2(v0, v1));
-        } else if (active && (v0 != 0.f || v1 != 0.f)) {
-            atomicAdd(base + key, make_float2(v0, v1));
+        }
+        if (!issue) continue;
+        const uint32_t i0 = hg_index(cw.c[0], cy, cz, L), i1 = hg_index(cw.c[0] + 1, cy, cz, L);
+        const bool nz0 = v00 != 0.f || v01 != 0.f, nz1 = v10 != 0.f || v11 != 0.f;
+        if (i1 == (i0 ^ 1u) && (nz0 || nz1)) {
+            const bool lo = (i0 & 1u) == 0u;      // i0 is the even (first) entry of the pair
+            atomicAdd(reinterpret_cast<float4*>(base + (i0 & ~1u)), lo ? make_float4(v00, v01, v10, v11) : make_float4(v10, v11, v00, v01));
+        } else {
+            if (nz0) atomicAdd(base + i0, make_float2(v00, v01));
+            if (nz1) atomicAdd(base + i1, make_float2(v10, v11));
         }
     }
 }
@@ -1500,7 +1518,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 for (int e = 0; e < e_end; e++, it++) {
                     const uint32_t par = it & 1;
                     tc::mbar_wait(a1_full, par); tc::tc_fence_after();
-                    issue_bf16x3(tmem + cD1, Ek, W1k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F1 (K = 32 + 32 zero columns)
+                    issue_bf16x3(tmem + cD1, Ek, W1k, 32, idesc_bf16(128, 64, 0, 0), 0);           // F1 (K = 32: the zero columns 32..63 of the tiles are skipped)
                     tc::umma_commit(d1_full);
                     tc::mbar_wait(a2_full, par); tc::tc_fence_after();
                     issue_bf16x3(tmem + cD2, Hk, W2k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F2
