@@ -236,7 +236,19 @@ def run_ours(args):
         step(args.warmup + s, False)
     torch.cuda.synchronize()
     gemm_ms, gemm_n = C.c_float(0), C.c_int(0)
+    dump_path = os.path.join(ROOT, "gpurun_out", f"sd_launches_rank{rank}.txt")
+    os.makedirs(os.path.dirname(dump_path), exist_ok=True)
+    os.environ["MI3D_SD_PROFILE_DUMP"] = dump_path          # one line per timed launch: M N K block_n splits conv batch epi ms
     L.check(L.lib().mi3d_sd_profile(guidance.engine.h, C.c_int(0), C.byref(gemm_ms), C.byref(gemm_n)), "sd_profile")
+    tile_flops = attn_flops = attn_ms = 0.0
+    attn_n = 0
+    for ln in open(dump_path):
+        f = ln.split()
+        Mm, Nn, Kk, conv, batch, ms_l = int(f[0]), int(f[1]), int(f[2]), int(f[5]), int(f[6]), float(f[8])
+        if conv == 2:
+            attn_flops += 4.0 * Mm * Nn * Kk * batch; attn_ms += ms_l; attn_n += 1
+        else:
+            tile_flops += 2.0 * Mm * Nn * Kk * batch
     prof_rows = field_ops.PROFILE
     field_ops.PROFILE = None
     for s in range(2):                      # untimed: first-use allocations of the host-input staging path
@@ -283,15 +295,19 @@ def run_ours(args):
     except Exception:
         pass
     gemm_ms_step = gemm_ms.value / n_prof
-    flops = 3.842e12
+    flops = tile_flops / n_prof          # 2 M N K of every tile-kernel launch of one step (the engine's own launch list)
     line["roofline"] = {
-        "kernel": "tc::k_tc_gemm<64|128|256> (tcgen05.mma/TMEM/TMA tile kernel; all launches of one step)", "bound": "tensor",
+        "kernel": "tc::k_tc_gemm<64|128|160|256> (tcgen05.mma/TMEM/TMA tile kernel; all launches of one step: every conv / linear of the U-Net and the VAE)", "bound": "tensor",
         "achieved": round(flops / (gemm_ms_step * 1e-3) / 1e12, 1), "peak": tf_peak, "unit": "TFLOP/s",
         "frac": round(flops / (gemm_ms_step * 1e-3) / 1e12 / tf_peak, 4),
         "traffic": summary.get("k_tc_gemm", {}).get("dram_bytes_per_launch"),
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured; kernel timed inside a long step)" if peaks else "fallback 1400 TFLOP/s (of fallback)",
         "ms_per_step": round(gemm_ms_step, 3), "launches_per_step": gemm_n.value // n_prof, "algorithmic_flops_per_step": flops,
     }
+    if attn_n:
+        line["roofline"]["attention"] = {"kernel": "attn::k_flash_attn (tcgen05, scores in TMEM)", "ms_per_step": round(attn_ms / n_prof, 3),
+                                         "launches_per_step": attn_n // n_prof, "achieved": round(attn_flops / (attn_ms * 1e-3) / 1e12, 1), "unit": "TFLOP/s",
+                                         "frac": round(attn_flops / (attn_ms * 1e-3) / 1e12 / tf_peak, 4)}
     # second roofline: the render kernels against the HBM roofline the north_star names (algorithmic bytes of SURVEY 8d;
     # these kernels are really bound by L1 gather / RED-atomic throughput)
     rk = {k: round(float(np.median(v)), 3) for k, v in per_kernel.items()}

@@ -298,7 +298,18 @@ struct Engine {
         if (dry) return;
         attn::Maps m;
         if (int r = attn::make_maps(&m, q, ldq, k, ldk, v, ldv, B, T, Tk, heads)) { err = r; return; }
-        push([=](cudaStream_t st) { return attn::launch(m, o, C, B, T, Tk_valid, heads, st); });
+        push([=](cudaStream_t st) {
+            if (!profile) return attn::launch(m, o, C, B, T, Tk_valid, heads, st);
+            // profiling: same event bracket as the tile kernel; recorded with conv = 2 (M = queries, N = keys, K = head_dim, batch = B * heads)
+            if (prof_used == prof_events.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); prof_events.push_back({a, b}); }
+            if (prof_shapes.size() < prof_events.size()) prof_shapes.resize(prof_events.size());
+            prof_shapes[prof_used] = {T, Tk_valid, 64, 0, 1, 2, B * heads, 0};
+            auto& ev = prof_events[prof_used++];
+            cudaEventRecord(ev.first, st);
+            const int r = attn::launch(m, o, C, B, T, Tk_valid, heads, st);
+            cudaEventRecord(ev.second, st);
+            return r;
+        });
     }
 
     T4 transformer(const std::string& pre, const T4& x, int heads) {
@@ -987,19 +998,19 @@ int mi3d_sd_profile(mi3d_sd_t h, int enable, float* gemm_ms, int* launches) {
     sd::Engine& e = h->e;
     if (enable) { e.profile = true; e.prof_used = 0; return MI3D_OK; }
     e.profile = false;
-    float total = 0.f;
+    float total = 0.f; int n_tile = 0;
     const char* dump = getenv("MI3D_SD_PROFILE_DUMP");        // tools/: one line per launch "M N K block_n splits conv batch epi ms"
     FILE* f = dump ? fopen(dump, "w") : nullptr;
     for (size_t i = 0; i < e.prof_used; i++) {
         float ms = 0.f;
         MI3D_CHECK(cudaEventSynchronize(e.prof_events[i].second));
         MI3D_CHECK(cudaEventElapsedTime(&ms, e.prof_events[i].first, e.prof_events[i].second));
-        total += ms;
+        if (e.prof_shapes[i].conv != 2) { total += ms; n_tile++; }
         if (f) { const auto& q = e.prof_shapes[i]; fprintf(f, "%d %d %d %d %d %d %d %d %.4f\n", q.M, q.N, q.K, q.bn, q.splits, q.conv, q.batch, q.epi, ms); }
     }
     if (f) fclose(f);
     if (gemm_ms) *gemm_ms = total;
-    if (launches) *launches = (int)e.prof_used;
+    if (launches) *launches = n_tile;
     return MI3D_OK;
 }
 

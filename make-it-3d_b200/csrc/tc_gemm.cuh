@@ -134,6 +134,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// issue only (no wait): lets the next chunk's TMEM read overlap the arithmetic / stores of the current one
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, 128B-swizzled operand tile descriptor (cute::UMMA::SmemDescriptor layout, version 1):
 //   start_address[0,14) = addr >> 4 ; LBO[16,30) = 1 ; SBO[32,46) = 1024 >> 4 (8 rows x 128 B) ; version[46,48) = 1 ;
 //   layout_type[61,64) = 2 (SWIZZLE_128B)
@@ -271,29 +285,38 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             const bool row_ok = m < p.m_valid;
             const size_t zoff = (size_t)(z % p.out_z1) * p.out_s_lo + (size_t)(z / p.out_z1) * p.out_s_hi;
             const float* rb = (p.row_bias && row_ok) ? p.row_bias + (size_t)(((long long)z * p.M + m) / p.rows_per_group) * p.N : nullptr;
-            #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v);
+            const uint32_t t_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
+            // one 32-column chunk: registers -> (alpha, bias, row bias, residual / GEGLU) -> global.  v is consumed before the call returns.
+            auto chunk = [&](const uint32_t (&v)[32], const int c0) {
                 const int n0 = n_blk * BLOCK_N + c0;
                 if (p.splits > 1) {
-                    // split-K partial: fp32 RED into the workspace; bias / residual / conversion happen in k_splitk_finish
+                    // split-K partial: fp32 RED (16 bytes each) into the workspace; bias / residual / conversion happen in k_splitk_finish
                     if (row_ok) {
-                        float* wsp = p.splitk_ws + (size_t)m * p.N + n0;
+                        float4* wsp = reinterpret_cast<float4*>(p.splitk_ws + (size_t)m * p.N + n0);
                         #pragma unroll
-                        for (int i = 0; i < 32; i++) atomicAdd(wsp + i, __uint_as_float(v[i]));
+                        for (int q = 0; q < 8; q++)
+                            atomicAdd(wsp + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
                     }
-                    continue;
+                    return;
                 }
                 float f[32];
                 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    float x = __uint_as_float(v[i]) * p.alpha;
-                    if (p.bias) x += __ldg(p.bias + n0 + i);
-                    if (rb) x += __ldg(rb + n0 + i);
-                    f[i] = x;
+                for (int i = 0; i < 32; i++) f[i] = __uint_as_float(v[i]) * p.alpha;
+                if (p.bias) {          // 16-byte loads (launch() checks the alignment): 8 instead of 32 load + address instructions per chunk
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + q);
+                        f[4 * q] += bv.x; f[4 * q + 1] += bv.y; f[4 * q + 2] += bv.z; f[4 * q + 3] += bv.w;
+                    }
                 }
-                if (!row_ok) continue;
+                if (rb) {
+                    #pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + n0) + q);
+                        f[4 * q] += bv.x; f[4 * q + 1] += bv.y; f[4 * q + 2] += bv.z; f[4 * q + 3] += bv.w;
+                    }
+                }
+                if (!row_ok) return;
                 if (p.epi_mode == EPI_GEGLU) {
                     // weight rows were interleaved (value, gate) at plan time: out[:, n/2] = value * gelu(gate)
                     __half* o = p.out + zoff + (size_t)m * p.ldc + (n0 >> 1);
@@ -330,6 +353,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         #pragma unroll
                         for (int q = 0; q < 4; q++) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(h)[q];
                     }
+                }
+            };
+            // software pipeline over the chunks: the TMEM read of chunk c+1 is in flight while chunk c is converted and stored
+            constexpr int NC = BLOCK_N / 32;
+            uint32_t va[32], vb[32];
+            tmem_ld32_issue(t_acc, va);
+            #pragma unroll 1
+            for (int c = 0; c < NC; c += 2) {
+                tmem_ld_wait();
+                if (c + 1 < NC) tmem_ld32_issue(t_acc + (uint32_t)((c + 1) * 32), vb);
+                chunk(va, c * 32);
+                if (c + 1 < NC) {
+                    tmem_ld_wait();
+                    if (c + 2 < NC) tmem_ld32_issue(t_acc + (uint32_t)((c + 2) * 32), va);
+                    chunk(vb, (c + 1) * 32);
                 }
             }
             // release this accumulator stage to the MMA warp (one arrive per epilogue warp)

@@ -83,6 +83,7 @@ inline int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const GemmPar
 
 inline int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int block_n, int batch, cudaStream_t st) {
     if (p.K % BLOCK_K || p.N % block_n || p.out_z1 < 1) return MI3D_ERR_ARG;
+    if (((uintptr_t)p.bias | (uintptr_t)p.row_bias | (uintptr_t)p.splitk_ws) & 15) return MI3D_ERR_ARG;     // read / RED-added 16 bytes at a time
     switch (block_n) {
         case 64: return launch_bn<64>(ma, mb, p, batch, st);
         case 128: return launch_bn<128>(ma, mb, p, batch, st);
