@@ -31,6 +31,7 @@ struct Params {
     __half* o;          // [B*T, ldo], head h at column h * 64
 };
 
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }   // one MUFU, no range fix-up
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -139,46 +140,53 @@ k_flash_attn(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             const int kbase = j * 128;
             const bool edge = kbase + 128 > p.kv_valid;
             float mx = -INFINITY;
-            #pragma unroll 1
-            for (int cc = 0; cc < 4; cc++) {
-                uint32_t v[32];
-                tmem_ld32(t_row + (uint32_t)(cc * 32), v);
-                #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    float s = __uint_as_float(v[i]);
-                    if (edge && kbase + cc * 32 + i >= p.kv_valid) s = -INFINITY;
-                    mx = fmaxf(mx, s);
-                }
+            {   // pass 1: row maximum; the TMEM read of chunk cc+1 is in flight while chunk cc is reduced
+                uint32_t va[32], vb[32];
+                auto red = [&](const uint32_t (&v)[32], const int cc) {
+                    #pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        float s = __uint_as_float(v[i]);
+                        if (edge && kbase + cc * 32 + i >= p.kv_valid) s = -INFINITY;
+                        mx = fmaxf(mx, s);
+                    }
+                };
+                tmem_ld32_issue(t_row, va); tmem_ld_wait();
+                tmem_ld32_issue(t_row + 32u, vb); red(va, 0); tmem_ld_wait();
+                tmem_ld32_issue(t_row + 64u, va); red(vb, 1); tmem_ld_wait();
+                tmem_ld32_issue(t_row + 96u, vb); red(va, 2); tmem_ld_wait();
+                red(vb, 3);
             }
             const float m_new = fmaxf(m, mx);
             const float mc = m_new * c;
-            const float alpha = exp2f(m * c - mc);                 // first block: exp2(-inf) = 0
+            const float alpha = ex2(m * c - mc);                   // first block: ex2(-inf) = 0
             float rs = 0.f;
-            #pragma unroll 1
-            for (int cc = 0; cc < 4; cc++) {
-                uint32_t v[32];
-                tmem_ld32(t_row + (uint32_t)(cc * 32), v);
-                uint8_t* atom = prow + (cc >> 1) * kTile;
-                #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    __align__(16) __half2 h2[4];
+            {   // pass 2: P = ex2(s c - m c) -> fp16 -> swizzled shared memory (A operand of the second product), row sum
+                uint32_t va[32], vb[32];
+                auto emit = [&](const uint32_t (&v)[32], const int cc) {
+                    uint8_t* atom = prow + (cc >> 1) * kTile;
                     #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        float s0 = __uint_as_float(v[g * 8 + 2 * i]), s1 = __uint_as_float(v[g * 8 + 2 * i + 1]);
-                        float p0 = exp2f(s0 * c - mc), p1 = exp2f(s1 * c - mc);
-                        if (edge) {
-                            const int col = kbase + cc * 32 + g * 8 + 2 * i;
-                            if (col >= p.kv_valid) p0 = 0.f;
-                            if (col + 1 >= p.kv_valid) p1 = 0.f;
+                    for (int g = 0; g < 4; g++) {
+                        __align__(16) __half2 h2[4];
+                        #pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            float p0 = ex2(fmaf(__uint_as_float(v[g * 8 + 2 * i]), c, -mc)), p1 = ex2(fmaf(__uint_as_float(v[g * 8 + 2 * i + 1]), c, -mc));
+                            if (edge) {
+                                const int col = kbase + cc * 32 + g * 8 + 2 * i;
+                                if (col >= p.kv_valid) p0 = 0.f;
+                                if (col + 1 >= p.kv_valid) p1 = 0.f;
+                            }
+                            h2[i] = __floats2half2_rn(p0, p1);
+                            rs += p0 + p1;
                         }
-                        h2[i] = __floats2half2_rn(p0, p1);
-                        // the sum runs over the fp16-rounded probabilities the tensor core will actually multiply
-                        const float2 pr = __half22float2(h2[i]);
-                        rs += pr.x + pr.y;
+                        const int chunk = (cc & 1) * 4 + g;            // 16-byte chunk inside the 128-byte row of this atom
+                        *reinterpret_cast<uint4*>(atom + ((chunk ^ rx) << 4)) = *reinterpret_cast<const uint4*>(h2);
                     }
-                    const int chunk = (cc & 1) * 4 + g;            // 16-byte chunk inside the 128-byte row of this atom
-                    *reinterpret_cast<uint4*>(atom + ((chunk ^ rx) << 4)) = *reinterpret_cast<const uint4*>(h2);
-                }
+                };
+                tmem_ld32_issue(t_row, va); tmem_ld_wait();
+                tmem_ld32_issue(t_row + 32u, vb); emit(va, 0); tmem_ld_wait();
+                tmem_ld32_issue(t_row + 64u, va); emit(vb, 1); tmem_ld_wait();
+                tmem_ld32_issue(t_row + 96u, vb); emit(va, 2); tmem_ld_wait();
+                emit(vb, 3);
             }
             l = l * alpha + rs;
             m = m_new;
@@ -187,12 +195,11 @@ k_flash_attn(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             mbar_arrive(p_full);
             mbar_wait(pv_full, (uint32_t)j & 1u);
             tc_fence_after();
-            #pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                uint32_t v[32];
-                tmem_ld32(t_row + 128u + (uint32_t)(cc * 32), v);
+            {
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(t_row + 128u, va); tmem_ld32_issue(t_row + 160u, vb); tmem_ld_wait();
                 #pragma unroll
-                for (int i = 0; i < 32; i++) O[cc * 32 + i] = O[cc * 32 + i] * alpha + __uint_as_float(v[i]);
+                for (int i = 0; i < 32; i++) { O[i] = fmaf(O[i], alpha, __uint_as_float(va[i])); O[32 + i] = fmaf(O[32 + i], alpha, __uint_as_float(vb[i])); }
             }
             tc_fence_before();
             mbar_arrive(pv_empty);
