@@ -150,3 +150,29 @@ def test_flash_attention_matches_fp32_reference(L, B, T, Tk, valid, heads):
     ref = ref.permute(0, 2, 1, 3).reshape(B * T, C_)
     err = (o.float() - ref).abs().max().item()
     assert err < 3e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_flash_attention_lazy_rescale(L):
+    """Logits that keep growing along the key axis force the lazy-rescale path (O row in TMEM multiplied by alpha) in every block;
+    logits that shrink never trigger it.  Both must match the fp32 reference."""
+    B, T, heads, C_ = 1, 256, 2, 128
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for sign in (+1.0, -1.0):
+        q = torch.zeros(B * T, C_, device="cuda")
+        q[:, 0] = 8.0; q[:, 64] = 8.0                      # every query: logit = ramp(key) (1/8 scale folded in)
+        k = torch.randn(B * 1024, C_, device="cuda", generator=g) * 0.05
+        ramp = sign * torch.linspace(0.0, 60.0, 1024, device="cuda")
+        k[:, 0] = ramp; k[:, 64] = ramp
+        v = torch.randn(B * 1024, C_, device="cuda", generator=g)
+        qh, kh, vh = q.half(), k.half(), v.half()
+        o = torch.zeros(B * T, C_, dtype=torch.float16, device="cuda")
+        L.check(L.lib().mi3d_flash_attn_f16(L.ptr(qh), L.ptr(kh), L.ptr(vh), L.ptr(o), C.c_int(B), C.c_int(T), C.c_int(1024), C.c_int(1024), C.c_int(heads),
+                                            C.c_int(C_), C.c_int(C_), C.c_int(C_), C.c_int(C_), L.stream()), "flash_attn")
+        torch.cuda.synchronize()
+        qf = qh.float().view(B, T, heads, 64).permute(0, 2, 1, 3)
+        kf = kh.float().view(B, 1024, heads, 64).permute(0, 2, 1, 3)
+        vf = vh.float().view(B, 1024, heads, 64).permute(0, 2, 1, 3)
+        ref = (torch.softmax(qf @ kf.transpose(-1, -2) / 8.0, dim=-1) @ vf).permute(0, 2, 1, 3).reshape(B * T, C_)
+        assert torch.isfinite(o).all()
+        err = (o.float() - ref).abs().max().item()
+        assert err < 3e-3 * max(1.0, ref.abs().max().item()), (sign, err)
