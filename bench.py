@@ -211,6 +211,15 @@ def run_ours(args):
     for s in range(max(args.warmup, 3)):
         step(s, False)
     torch.cuda.synchronize()
+    if args.launch_list:
+        torch.cuda.nvtx.range_push("timed_steps")
+        for s in range(args.steps):
+            step(args.warmup + s, False)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     # ---- launch count (one profiled step, outside the timed region) ----
     launches_per_step = None
     try:
@@ -384,6 +393,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--launch-list", action="store_true",
+                    help="profiling aid: warm up, run --steps steps of the same step function and exit (use under "
+                         "`ncu --metrics gpu__time_duration.sum`; numbers printed under a profiler are never bench values)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -747,10 +747,35 @@ struct Engine {
         return err;
     }
 
-    int run(std::vector<Op>& ops, cudaStream_t st) {
+    int run_eager(std::vector<Op>& ops, cudaStream_t st) {
         for (auto& op : ops) { int r = op(st); if (r) return r; }
         return MI3D_OK;
     }
+    // The launch lists are static (fixed pointers, shapes and order; the timestep and every input live in device buffers), so from
+    // the second call on each list is replayed as one CUDA graph: ~200-330 launches per list lose their per-kernel CPU launch
+    // cost and most of the inter-kernel gap.  Profiling (events inside the ops) and MI3D_SD_GRAPH=0 use the eager path.
+    struct ListGraph { cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; };
+    std::map<std::vector<Op>*, ListGraph> graphs;
+    int run(std::vector<Op>& ops, cudaStream_t st) {
+        static int use = -1;
+        if (use < 0) { const char* e = getenv("MI3D_SD_GRAPH"); use = (e && e[0] == '0') ? 0 : 1; }
+        ListGraph& g = graphs[&ops];
+        if (!use || profile || g.failed) return run_eager(ops, st);
+        if (g.exec) return (int)cudaGraphLaunch(g.exec, st);
+        if (g.calls++ == 0) return run_eager(ops, st);            // first call: plain launches (one-time function attributes, warm caches)
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g.failed = true; return run_eager(ops, st); }
+        const int r = run_eager(ops, st);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (r || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError(); g.failed = true; g.exec = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+            return r ? r : run_eager(ops, st);
+        }
+        cudaGraphDestroy(graph);
+        return (int)cudaGraphLaunch(g.exec, st);
+    }
+    ~Engine() { for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); }
 };
 
 // ------------------------------------------------------------------------------------------------------------
