@@ -751,14 +751,16 @@ struct Engine {
         for (auto& op : ops) { int r = op(st); if (r) return r; }
         return MI3D_OK;
     }
-    // The launch lists are static (fixed pointers, shapes and order; the timestep and every input live in device buffers), so from
-    // the second call on each list is replayed as one CUDA graph: ~200-330 launches per list lose their per-kernel CPU launch
-    // cost and most of the inter-kernel gap.  Profiling (events inside the ops) and MI3D_SD_GRAPH=0 use the eager path.
+    // The launch lists are static (fixed pointers, shapes and order; the timestep and every input live in device buffers), so a list
+    // can be replayed as one CUDA graph from its second call on (~200-330 launches lose their CPU launch cost).  OPT-IN
+    // (MI3D_SD_GRAPH=1) and only on a capturable stream: torch's default stream is the legacy stream, which cannot be captured, so
+    // the bench / tests run the eager path; measured there, the lists are bound by kernel latency, not by launch gaps (graph
+    // replay on a side stream: 7.58 vs 7.58 ms for the U-Net pass).
     struct ListGraph { cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; };
     std::map<std::vector<Op>*, ListGraph> graphs;
     int run(std::vector<Op>& ops, cudaStream_t st) {
         static int use = -1;
-        if (use < 0) { const char* e = getenv("MI3D_SD_GRAPH"); use = (e && e[0] == '0') ? 0 : 1; }
+        if (use < 0) { const char* e = getenv("MI3D_SD_GRAPH"); use = (e && e[0] == '1') ? 1 : 0; }
         ListGraph& g = graphs[&ops];
         if (!use || profile || g.failed) return run_eager(ops, st);
         if (g.exec) return (int)cudaGraphLaunch(g.exec, st);
