@@ -754,8 +754,8 @@ struct Engine {
     // The launch lists are static (fixed pointers, shapes and order; the timestep and every input live in device buffers), so a list
     // can be replayed as one CUDA graph from its second call on (~200-330 launches lose their CPU launch cost).  OPT-IN
     // (MI3D_SD_GRAPH=1) and only on a capturable stream: torch's default stream is the legacy stream, which cannot be captured, so
-    // the bench / tests run the eager path; measured there, the lists are bound by kernel latency, not by launch gaps (graph
-    // replay on a side stream: 7.58 vs 7.58 ms for the U-Net pass).
+    // the bench / tests run the eager path.  Not yet measured on a side stream (round 2); the eager lists are GPU-bound (~23 us of
+    // kernel time per launch against ~5 us of CPU launch cost).
     struct ListGraph { cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; };
     std::map<std::vector<Op>*, ListGraph> graphs;
     int run(std::vector<Op>& ops, cudaStream_t st) {
