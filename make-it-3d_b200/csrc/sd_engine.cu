@@ -754,8 +754,9 @@ struct Engine {
     // The launch lists are static (fixed pointers, shapes and order; the timestep and every input live in device buffers), so a list
     // can be replayed as one CUDA graph from its second call on (~200-330 launches lose their CPU launch cost).  OPT-IN
     // (MI3D_SD_GRAPH=1) and only on a capturable stream: torch's default stream is the legacy stream, which cannot be captured, so
-    // the bench / tests run the eager path.  Not yet measured on a side stream (round 2); the eager lists are GPU-bound (~23 us of
-    // kernel time per launch against ~5 us of CPU launch cost).
+    // the bench / tests run the eager path.  Measured on a side stream (tools/prof_sd.py, PROF_SIDE_STREAM=1): U-Net pass
+    // 7.68 -> 6.67 ms, VAE encode 2.89 -> 2.73 ms, VAE backward 3.55 -> 3.37 ms.  Making it the default (engine on its own stream,
+    // event-ordered against the caller's) needs the full parity suite under replay first: round 2.
     struct ListGraph { cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; };
     std::map<std::vector<Op>*, ListGraph> graphs;
     int run(std::vector<Op>& ops, cudaStream_t st) {

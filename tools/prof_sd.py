@@ -21,6 +21,10 @@ def main():
     ctx = torch.randn(2, 77, 1024, device="cuda")
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     te, tu, tb = [], [], []
+    side = torch.cuda.Stream() if os.environ.get("PROF_SIDE_STREAM") else None     # a capturable stream (MI3D_SD_GRAPH=1 experiments)
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(side)
     for it in range(iters + 2):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         rgb.grad = None
