@@ -13,8 +13,10 @@ What is NOT built ("next"): the text encoder, VAE decoder a
 (nerf/sd.py:153-159).  That branch yields no gradient to any optimised parameter; here it returns (0, None) without
 running, which leaves the optimisation trajectory identical.
 """
+import contextlib
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -96,6 +98,22 @@ class SDEngine:
             r = lib.mi3d_sd_param_shape(self.h, C.c_int(i), shp)
             self.shapes.append(tuple(shp[k] for k in range(r)))
         self.nbytes = nbytes
+        # Opt-in (MI3D_SD_STREAM=1, together with MI3D_SD_GRAPH=1): run the launch lists on the engine's own stream.  torch's default
+        # stream is the legacy stream, which CUDA cannot capture; on a side stream the lists replay as graphs (measured
+        # -1.35 ms per guidance step, tools/prof_sd.py).  Off by default until the parity suite has run under replay.
+        self.stream = torch.cuda.Stream(device) if os.environ.get("MI3D_SD_STREAM") == "1" else None
+
+    @contextlib.contextmanager
+    def on_stream(self):
+        """Engine calls inside run on self.stream, ordered after the caller's pending work; the caller's stream then waits for them."""
+        if self.stream is None:
+            yield
+            return
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            yield
+        cur.wait_stream(self.stream)
 
     def load(self, tensors):
         """tensors: name -> fp32 CUDA tensor in diffusers layout (VAE names as in AutoencoderKL.state_dict())."""
@@ -152,7 +170,8 @@ class _EncodeImgs(torch.autograd.Function):
             raise L.Mi3dError("encode_imgs expects pred_rgb [1,3,H,W]")
         hw = engine.v.image_hw // 8
         latents = torch.empty(1, 4, hw, hw, dtype=torch.float32, device=pred_rgb.device)
-        L.check(L.lib().mi3d_sd_encode(engine.h, L.ptr(pred_rgb), C.c_int(H), C.c_int(W), L.ptr(eps), L.ptr(latents), L.stream()), "sd_encode")
+        with engine.on_stream():
+            L.check(L.lib().mi3d_sd_encode(engine.h, L.ptr(pred_rgb), C.c_int(H), C.c_int(W), L.ptr(eps), L.ptr(latents), L.stream()), "sd_encode")
         ctx.engine, ctx.hw_in = engine, (H, W)
         ctx.save_for_backward(eps)
         return latents
@@ -163,8 +182,9 @@ class _EncodeImgs(torch.autograd.Function):
         H, W = ctx.hw_in
         g = L.f32c(g)
         grad = torch.empty(1, 3, H, W, dtype=torch.float32, device=g.device)
-        L.check(L.lib().mi3d_sd_encode_backward(ctx.engine.h, L.ptr(g), L.ptr(eps), C.c_int(H), C.c_int(W), L.ptr(grad), L.stream()),
-                "sd_encode_backward")
+        with ctx.engine.on_stream():
+            L.check(L.lib().mi3d_sd_encode_backward(ctx.engine.h, L.ptr(g), L.ptr(eps), C.c_int(H), C.c_int(W), L.ptr(grad), L.stream()),
+                    "sd_encode_backward")
         return grad, None, None
 
 
@@ -238,8 +258,9 @@ class StableDiffusion(nn.Module):
         latents, noise, text_embeddings = L.f32c(latents.detach()), L.f32c(noise), L.f32c(text_embeddings)
         noise_pred = torch.empty_like(latents)
         grad = torch.empty_like(latents)
-        L.check(L.lib().mi3d_sd_unet_sds(self.engine.h, L.ptr(latents), L.ptr(noise), L.ptr(t), L.ptr(self.alphas), L.ptr(text_embeddings),
-                                         C.c_float(float(guidance_scale)), L.ptr(noise_pred), L.ptr(grad), L.stream()), "sd_unet_sds")
+        with self.engine.on_stream():
+            L.check(L.lib().mi3d_sd_unet_sds(self.engine.h, L.ptr(latents), L.ptr(noise), L.ptr(t), L.ptr(self.alphas), L.ptr(text_embeddings),
+                                             C.c_float(float(guidance_scale)), L.ptr(noise_pred), L.ptr(grad), L.stream()), "sd_unet_sds")
         return noise_pred, grad
 
     def train_step(self, text_embeddings, pred_rgb, ref_rgb=None, noise=None, islarge=False, ref_text=None, clip_model=None,
