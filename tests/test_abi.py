@@ -67,3 +67,34 @@ def test_state_dict_keys_match_reference(mi3d):
             'sigma_net.net.1.weight': (64, 64), 'sigma_net.net.1.bias': (64,), 'sigma_net.net.2.weight': (4, 64),
             'sigma_net.net.2.bias': (4,)}
     assert {k: tuple(v.shape) for k, v in sd.items()} == want
+
+
+def test_committed_bench_line_has_every_contract_key():
+    """profiles/r1_final_bench.json is the last line bench.py printed on a B200: the keys the driver parses must all be there"""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_final_bench.json")
+    line = json.loads(open(path).read())
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["config"]["workload"] and "model" not in line["config"]
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-3
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert line["gpu_launches"] > 0 and not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_engine_stream_context_is_a_no_op_by_default():
+    """MI3D_SD_STREAM unset: SDEngine.on_stream() must not touch streams (the engine then launches on the caller's stream)"""
+    import importlib
+    sd = importlib.import_module("make-it-3d_b200.nerf.sd")
+
+    class _E:
+        stream = None
+    ran = []
+    with sd.SDEngine.on_stream(_E()):
+        ran.append(1)
+    assert ran == [1]
