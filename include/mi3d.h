@@ -48,8 +48,11 @@ int mi3d_packbits(const float* grid, uint32_t n_bytes, float thresh, const float
  *    min_near is fused into the kernel (optionally written to nears_out/fars_out, nullable).
  *  - noises: [N] U[0,1) (raymarching.py:226) or NULL -> in-kernel Philox keyed by (seed, ray id).
  *  - rays[n] = (n, offset, count): compaction is ordered by ray id (deterministic), not by atomic arrival.
- *  - counter[0] += total samples, counter[1] += N (caller zeroes it like renderer.py:504).
- *  - M = capacity of xyzs/dirs/deltas in rows; rays that do not fit write nothing (raymarching.cu:416).
+ *  - counter[0] += EMITTED samples, counter[1] += N (caller zeroes it like renderer.py:504).
+ *  - M = capacity of xyzs/dirs/deltas in rows; rays that do not fit write nothing (raymarching.cu:416).  Because
+ *    offsets are ordered by ray id the emitted samples are always the contiguous prefix [0, counter[0]) -- on overflow
+ *    counter[0] is the offset of the first dropped ray, not the uncapped total the reference adds (raymarching.cu:405):
+ *    nothing is zero-filled here, so consumers must never see the unwritten rows.
  *  - workspace: mi3d_march_rays_train_workspace_bytes(N) bytes (zero-filled internally). */
 size_t mi3d_march_rays_train_workspace_bytes(uint32_t N);
 int mi3d_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield, float bound,
@@ -59,6 +62,28 @@ int mi3d_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
                           float* xyzs, float* dirs, float* deltas, int* rays, int* counter,
                           void* workspace, mi3d_stream_t stream);
 
+/* Ray generation (replaces get_rays, nerf/utils.py:51-116, for the N = -1 "every pixel" mode training uses, provider.py:297).
+ * A batch holds n_views * rays_per_view rays: batch ray i belongs to view i / rays_per_view and to the row-major pixel
+ * (i % rays_per_view) * pixel_stride + pixel_phase of that view.  stride 1 / phase 0 / rays_per_view = H*W is one full image;
+ * stride G / phase r deals every G-th pixel of each of G views to rank r (ray-parallel render).
+ * cams: DEVICE [n_views][16] fp32 = rows 0..2 of the cam2world pose (3x4 row-major, R | t) followed by fx, fy, cx, cy. */
+typedef struct {
+    const float* cams;
+    uint32_t n_views;
+    uint32_t H, W;
+    uint32_t rays_per_view;
+    uint32_t pixel_stride, pixel_phase;
+} mi3d_raygen;
+/* rays_o / rays_d [N,3], depth_scale [N] (each nullable), N = n_views * rays_per_view */
+int mi3d_get_rays(const mi3d_raygen* rg, uint32_t N, float* rays_o, float* rays_d, float* depth_scale, mi3d_stream_t stream);
+/* mi3d_march_rays_train with the rays generated inside the kernel (no rays_o / rays_d tensors; near/far always fused):
+ * depth_scale_out [N] nullable.  The Philox march jitter (noises == NULL) is keyed by (view, pixel), not by the batch index. */
+int mi3d_march_rays_train_cam(const mi3d_raygen* rg, float* depth_scale_out, const uint8_t* density_bitfield, float bound,
+                              float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                              const float* aabb, float min_near, float* nears_out, float* fars_out, const float* noises,
+                              uint64_t seed, float* xyzs, float* dirs, float* deltas, int* rays, int* counter,
+                              void* workspace, mi3d_stream_t stream);
+
 /* Optional fused epilogue of NeRFRenderer.run_cuda (nerf/renderer.py:553-570):
  *   image_out = image + (1 - ws) * bg ;  depth_out = (depth + (1 - ws) * max_depth) * depth_scale */
 typedef struct {
@@ -66,6 +91,7 @@ typedef struct {
     float bg_scalar;
     float max_depth;          /* opt.max_depth, main.py:91 */
     const float* depth_scale; /* device [N] or NULL */
+    uint32_t rays_per_view;   /* > 0: multi-view batch, bg_color is [n_views][3] and ray n uses row n / rays_per_view; 0: one colour */
 } mi3d_epilogue;
 
 /* replaces composite_rays_train_forward, raymarching.cu:501-590 (raymarching.py:250-281).
@@ -124,6 +150,8 @@ typedef struct { const float *w1, *b1, *w2, *b2, *w3, *b3; } mi3d_mlp;
 typedef struct { float *w1, *b1, *w2, *b2, *w3, *b3; } mi3d_mlp_grad;
 
 enum { MI3D_SHADING_ALBEDO = 0, MI3D_SHADING_LAMBERTIAN = 1, MI3D_SHADING_TEXTURELESS = 2, MI3D_SHADING_NORMAL = 3 };
+/* kernel family of the fused field: tcgen05 split-precision tiles (default) or the register-tiled fp32 FFMA kernels */
+enum { MI3D_FIELD_IMPL_TCGEN05 = 0, MI3D_FIELD_IMPL_FFMA = 1 };
 
 typedef struct {
     float bound;          /* opt.bound */
@@ -133,8 +161,23 @@ typedef struct {
                              13: + the perturbed normal of the smoothness loss (renderer.py:521-524) */
     int shading;          /* MI3D_SHADING_* (network_tcnn.py:146-170) */
     float ambient_ratio;
-    const float* light_d; /* device [3], needed unless shading == albedo */
+    const float* light_d; /* device [3] (multi-view batches: [n_views][3]), needed unless shading == albedo */
+    int impl;             /* MI3D_FIELD_IMPL_* (explicit: the library reads no environment variables) */
 } mi3d_field_cfg;
+
+/* Multi-view batches (several camera views' rays in one march: ray-parallel multi-GPU render, or several views per GPU).
+ * Samples are emitted in ray order, hence grouped by view.  DEVICE table, written by mi3d_render_forward (phase SHADE):
+ *   rows [bounds[s], bounds[s+1]),  s <  n_views : the samples of view s in this batch
+ *                                   s >= n_views : zero rows of view s - n_views evaluated here (the reference pads every view's
+ *                                                  sample list to the next multiple of 128 with xyz = dir = 0 rows that take part
+ *                                                  in the loss means, raymarching.py:237-241; exactly one rank owns a view's)
+ *   mpad[v] : padded sample count of the WHOLE view v, summed over all ranks -- the denominator of its loss means. */
+#define MI3D_MAX_VIEWS 8
+typedef struct {
+    uint32_t n_views;
+    uint32_t bounds[2 * MI3D_MAX_VIEWS + 1];
+    uint32_t mpad[MI3D_MAX_VIEWS];
+} mi3d_view_segs;
 
 typedef struct {
     const float* xyzs;         /* [cap,3] sample positions (output of mi3d_march_rays_train) */
@@ -152,6 +195,12 @@ typedef struct {
     float* enc_cache;
     uint32_t enc_cache_tiles;
     uint32_t enc_cache_valid;
+    /* multi-view batch: DEVICE table (NULL = one view: counter / m_fixed / align above describe the rows) and its view count.
+     * With segs, loss_orient / loss_smooth / grad_loss_* are [n_views] arrays and loss_partials holds
+     * 2 * n_views * mi3d_field_grid_ctas(0) floats.  tcgen05 kernels only. */
+    const mi3d_view_segs* segs;
+    uint32_t n_views;
+    uint32_t noise_mode;       /* in-kernel smoothness perturbation keyed by 0: (seed, row)  1: (seed, sample position) */
 } mi3d_field_io;
 size_t mi3d_field_enc_cache_bytes(uint32_t tiles);
 
@@ -175,6 +224,76 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
  * pipeline per chunk of 1 048 576 samples (full-occupancy gather -> tensor-core chain -> full-occupancy warp-aggregated scatter);
  * when NULL everything stays in one kernel (slower: the gather/scatter warps are starved). */
 size_t mi3d_field_backward_workspace_bytes(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Fused render step: the training branch of NeRFRenderer.run_cuda (nerf/renderer.py:481-524,553-583) as one call per
+ * direction (SURVEY.md 8b "mi3d_render_fwd / mi3d_render_bwd").  Sequences the kernels behind the B1 / B2 entry points
+ * above over one caller-owned workspace; see csrc/render.cu for the multi-view / ray-parallel protocol.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    /* rays: explicit tensors, or generated in the march kernel from cameras when rays_o == NULL */
+    const float* rays_o;          /* [N,3] */
+    const float* rays_d;          /* [N,3] */
+    const float* depth_scale;     /* [N] or NULL (explicit rays only; generated rays carry their own) */
+    const mi3d_raygen* raygen;    /* HOST struct (its cams pointer is a device pointer) */
+    uint32_t N;
+    uint32_t n_views;             /* views in the batch, 1..MI3D_MAX_VIEWS; view of ray i = i / (N / n_views) */
+    /* occupancy grid + march (renderer.py:481-508; min_near is the wrapper default 0.2, raymarching.py:34) */
+    const uint8_t* density_bitfield;
+    uint32_t C, H;
+    float bound, dt_gamma;
+    uint32_t max_steps;
+    float min_near;
+    const float* aabb;            /* device [6] */
+    const float* noises;          /* [N] or NULL -> Philox(seed) */
+    uint64_t seed;
+    /* compositing + epilogue (renderer.py:553-570) */
+    float T_thresh;
+    const float* bg_color;        /* device [n_views][3] or NULL -> bg_scalar */
+    float bg_scalar;
+    float max_depth;
+    /* regularisers (renderer.py:513-524) */
+    const float* smooth_noise;    /* [cap,3] or NULL -> Philox(seed + 1) */
+    uint32_t noise_mode;          /* mi3d_field_io.noise_mode */
+    /* ray-parallel multi-rank render */
+    const int* all_counts;        /* DEVICE [n_ranks][n_views]: every rank's ws->view_counts, all-gathered; NULL = this rank holds whole views */
+    uint32_t n_ranks;
+    uint32_t pad_view_mask;       /* bit v set: this rank evaluates the 128-alignment zero rows of view v (exactly one rank per view) */
+} mi3d_render_args;
+
+typedef struct {                  /* filled by mi3d_render_workspace_carve; all DEVICE pointers into the caller's blob */
+    uint32_t N, cap, n_views;     /* cap = min(N * max_steps, max_samples) + 128 * n_views rows */
+    float *xyzs, *dirs, *deltas, *sigmas, *rgbs, *tape, *g_sigmas, *g_rgbs;        /* per sample */
+    int *rays, *counter;                                                            /* [N,3], [2]: counter[0] = emitted samples */
+    float *nears, *fars, *ws_raw, *depth_raw, *image_raw, *depth_scale;             /* per ray */
+    void* scan_ws;
+    float* loss_partials;
+    int* view_counts;             /* [MI3D_MAX_VIEWS] this rank's samples per view (written by phase MARCH of multi-view batches) */
+    mi3d_view_segs* segs;
+    float* enc_cache;
+    uint32_t enc_cache_tiles;
+    size_t bytes;
+} mi3d_render_ws;
+
+size_t mi3d_render_workspace_bytes(uint32_t N, uint32_t max_steps, uint32_t max_samples /* 0 = N * max_steps */, uint32_t n_views,
+                                   uint32_t enc_cache_tiles);
+int mi3d_render_workspace_carve(void* base, uint32_t N, uint32_t max_steps, uint32_t max_samples, uint32_t n_views,
+                                uint32_t enc_cache_tiles, mi3d_render_ws* out);
+
+enum { MI3D_RENDER_PHASE_MARCH = 1, MI3D_RENDER_PHASE_SHADE = 2, MI3D_RENDER_PHASE_ALL = 3 };
+/* image [N,3], depth [N], weights_sum [N]; loss_orient / loss_smooth: device scalars (one view, single rank) or [n_views] arrays
+ * of this rank's SHARE of every view's mean (multi-view: sum them over ranks).  phases: MARCH | SHADE; a multi-rank caller runs
+ * MARCH, all-gathers ws->view_counts into args->all_counts, then runs SHADE. */
+int mi3d_render_forward(const mi3d_render_args* args, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
+                        const mi3d_field_cfg* cfg, const mi3d_render_ws* ws, int phases, float* image, float* depth,
+                        float* weights_sum, float* loss_orient, float* loss_smooth, mi3d_stream_t stream);
+/* grad_image [N,3] required; grad_depth / grad_weights_sum [N] and grad_loss_* (scalars or [n_views]) nullable.  Accumulates (+=)
+ * into grad_table / grad_mlp.  enc_cache_valid: the workspace still holds this forward's encodings. */
+int mi3d_render_backward(const mi3d_render_args* args, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
+                         const mi3d_field_cfg* cfg, const mi3d_render_ws* ws, const float* grad_image, const float* grad_depth,
+                         const float* grad_weights_sum, const float* grad_loss_orient, const float* grad_loss_smooth,
+                         float* grad_table, const mi3d_mlp_grad* grad_mlp, void* bwd_workspace, int enc_cache_valid,
+                         mi3d_stream_t stream);
 
 /* Replaces NeRFRenderer.update_extra_state (nerf/renderer.py:587-637): density_grid [C,H^3] EMA-max update from the
  * field at jittered cell centres, mean density (device scalar out), bitfield repack.  jitter: [C,H^3,3] U[0,1) or NULL
@@ -273,6 +392,13 @@ int mi3d_sd_unet_sds(mi3d_sd_t h, const float* latents, const float* noise, cons
 /* live timing of the tensor-core tile kernel: enable=1 starts recording CUDA events around every launch; enable=0 stops and
  * returns the summed kernel time (ms) and launch count (HOST pointers; synchronises on the recorded events). */
 int mi3d_sd_profile(mi3d_sd_t h, int enable, float* gemm_ms_host, int* launches_host);
+/* same, and (enable=0) also writes one text line per timed launch to dump_path_host: "M N K block_n splits conv batch epi ms" */
+int mi3d_sd_profile_dump(mi3d_sd_t h, int enable, float* gemm_ms_host, int* launches_host, const char* dump_path_host);
+/* CUDA-graph replay of the three static launch lists (U-Net, VAE encode, VAE input-gradient): from its third call on a list is
+ * one cudaGraphLaunch.  `stream` of the run calls must then be capturable (not the legacy default stream).  Off by default at the
+ * C level; nerf/sd.py turns it on together with an engine-owned stream.  mi3d_sd_graph_replays: lists currently instantiated. */
+int mi3d_sd_set_graph_replay(mi3d_sd_t h, int enable);
+int mi3d_sd_graph_replays(mi3d_sd_t h);
 /* debug tap: device pointer + size of a named intermediate ("unet.mid", "vae.grad_in", ...) */
 int mi3d_sd_debug_tensor(mi3d_sd_t h, const char* name, void** ptr, size_t* bytes);
 

@@ -447,6 +447,56 @@ __device__ __forceinline__ void gauss_pair(uint64_t seed, uint32_t row, uint32_t
     out[0] = m1 * cospif(2.f * u2); out[1] = m1 * sinpif(2.f * u2); out[2] = m2 * cospif(2.f * u4);
 }
 
+// position-keyed variant: the draw is a pure function of (seed, sample position), i.e. independent of which rank / row evaluates
+// the sample (ray-parallel render: a G-rank step must equal the single-process accumulation of the same views)
+__device__ __forceinline__ void gauss_pos(uint64_t seed, const float x[3], float out[3]) {
+    const uint4 r = mi3d_philox(make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), 0x706f7321u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u1 = fmaxf(mi3d_u01(r.x), 5.9604645e-8f), u2 = mi3d_u01(r.y), u3 = fmaxf(mi3d_u01(r.z), 5.9604645e-8f), u4 = mi3d_u01(r.w);
+    const float m1 = sqrtf(-2.f * logf(u1)), m2 = sqrtf(-2.f * logf(u3));
+    out[0] = m1 * cospif(2.f * u2); out[1] = m1 * sinpif(2.f * u2); out[2] = m2 * cospif(2.f * u4);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row bookkeeping.  Single view: rows [0, M) are samples, [M, m_pad) the reference's zero rows (raymarching.py:237-241).
+// Multi-view batch (mi3d_view_segs): rows are ordered by ray id, hence by view; segment s < n_views holds the samples of view s,
+// segment n_views + v the zero rows of view v that THIS rank evaluates; every per-sample mean is over the whole view's padded
+// count mpad[v] (summed over ranks), so that sharding a view's rays over ranks changes nothing but the summation order.
+// ---------------------------------------------------------------------------------------------------------
+struct Rows { uint32_t M, m_pad; const mi3d_view_segs* segs; };
+struct RowInfo { bool in_range, real; uint32_t view, mpad, pad_idx; };
+
+__device__ __forceinline__ Rows rows_make(const int* counter, uint32_t m_fixed, uint32_t align, uint32_t cap, const mi3d_view_segs* segs) {
+    Rows R; R.segs = segs;
+    if (segs) { R.M = min(segs->bounds[segs->n_views], cap); R.m_pad = min(segs->bounds[2 * segs->n_views], cap); }
+    else { R.M = counter ? min((uint32_t)counter[0], cap) : m_fixed; R.m_pad = padded_rows(R.M, align, cap); }
+    return R;
+}
+
+__device__ __forceinline__ RowInfo row_info(const Rows& R, uint32_t row) {
+    RowInfo ri;
+    ri.in_range = row < R.m_pad; ri.real = row < R.M;
+    if (!R.segs) { ri.view = 0; ri.mpad = R.m_pad; ri.pad_idx = row - R.M; return ri; }
+    const uint32_t nv = R.segs->n_views;
+    uint32_t sgm = 0;
+    for (uint32_t j = 1; j < 2 * nv; j++) sgm += row >= R.segs->bounds[j] ? 1u : 0u;
+    ri.view = sgm < nv ? sgm : sgm - nv;
+    ri.mpad = R.segs->mpad[ri.view];
+    ri.pad_idx = row - R.segs->bounds[sgm];
+    return ri;
+}
+
+// smoothness-loss perturbation z ~ N(0,1)^3 of a row (renderer.py:522): injected array, Philox by row (single view), or Philox by
+// position (multi-view / noise_mode 1; a view's zero rows are keyed by their index among them) -- either way the draw of a sample
+// does not depend on which rank, batch or row evaluates it
+__device__ __forceinline__ void smooth_z(const float* __restrict__ smooth_noise, uint64_t seed, uint32_t noise_mode, uint32_t row,
+                                         const RowInfo& ri, const float x[3], float z[3]) {
+    if (smooth_noise) { z[0] = smooth_noise[3 * (size_t)row]; z[1] = smooth_noise[3 * (size_t)row + 1]; z[2] = smooth_noise[3 * (size_t)row + 2]; }
+    else if (noise_mode == 0) gauss_pair(seed, row, 1u, z);
+    else if (ri.real) gauss_pos(seed, x, z);
+    else gauss_pair(seed, ri.pad_idx, 2u, z);            // zero rows: keyed by their index among the view's zero rows
+}
+
 struct FwdArgs {
     const float* xyzs; const float* dirs; const int* counter; uint32_t m_fixed, align, cap;
     const float* table; mi3d_hashgrid hg; mi3d_mlp mlp;
@@ -455,6 +505,7 @@ struct FwdArgs {
     const float* smooth_noise; uint64_t seed;
     float* sigmas; float* rgbs; float* normals; float* tape; float* loss_partials;
     float* enc_cache; uint32_t enc_cache_tiles;     // optional: encodings of the first enc_cache_tiles tiles, laid out like the backward's enc_buf
+    const mi3d_view_segs* segs; uint32_t noise_mode; // multi-view batch (device table) / Philox keying of the smoothness perturbation
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -588,7 +639,7 @@ constexpr uint32_t kTmemCols = 256;
 constexpr int oA1H = 0, oA1L = oA1H + kA1, oA2H = oA1L + kA1, oA2L = oA2H + 2 * kA1;
 constexpr int oW1H = oA2L + 2 * kA1, oW1L = oW1H + 8192, oW2H = oW1L + 8192, oW2L = oW2H + 16384;
 constexpr int oW3H = oW2L + 16384, oW3L = oW3H + 4096, oMisc = oW3L + 4096;
-constexpr size_t kSmem = 1024 + oMisc + 1024;
+constexpr size_t kSmem = 1024 + oMisc + 2048;
 
 // D (+)= A[128 x 32*KB] . B[N x 32*KB]^T over hi/lo split tiles; a_hi/a_lo/b_hi/b_lo are smem addresses of the first K-block
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int kblocks,
@@ -619,6 +670,8 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oMisc + 896);   // a1_full, a1_empty, d1_full, a2_full, d2_full, a3_full, d3_full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     float* red = reinterpret_cast<float*>(tmem_slot + 2);       // [2][4] loss partials
+    float* s_loss = red + 8;                                    // [MI3D_MAX_VIEWS][2] per-view loss sums (multi-view batches)
+    __shared__ mi3d_view_segs segs_sm;
     uint64_t *a1_full = bars, *a1_empty = bars + 1, *d1_full = bars + 2, *a2_full = bars + 3, *d2_full = bars + 4, *a3_full = bars + 5, *d3_full = bars + 6;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -647,6 +700,8 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
         } else { L.offset = 0; L.size = 8; L.res = 2; L.scale = 1.f; L.hashed = 0; }
         lv[l] = L;
     }
+    if (a.segs && tid < (int)(sizeof(mi3d_view_segs) / 4)) reinterpret_cast<uint32_t*>(&segs_sm)[tid] = reinterpret_cast<const uint32_t*>(a.segs)[tid];
+    if (tid < 2 * MI3D_MAX_VIEWS) s_loss[tid] = 0.f;
     if (tid == 0) {
         tc::mbar_init(a1_full, 256); tc::mbar_init(a1_empty, 1); tc::mbar_init(d1_full, 1); tc::mbar_init(a2_full, 128);
         tc::mbar_init(d2_full, 1); tc::mbar_init(a3_full, 128); tc::mbar_init(d3_full, 1);
@@ -660,8 +715,8 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
     const uint32_t tmem = *tmem_slot;
     const uint32_t sbase = tc::smem_u32(sm);
 
-    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
-    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
+    const Rows R = rows_make(a.counter, a.m_fixed, a.align, a.cap, a.segs ? &segs_sm : nullptr);
+    const uint32_t m_pad = R.m_pad;
     const int n_evals = a.n_evals;
     const float inv2b = 2.f * a.bound;
     float acc_orient = 0.f, acc_smooth = 0.f;
@@ -671,12 +726,13 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
         // ================================ owners ================================
         const int r = tid;
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
-        float light[3] = {0.f, 0.f, 0.f};
-        if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
         for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
-            const bool in_range = row < m_pad, real = row < M;
+            const RowInfo ri = row_info(R, row);
+            const bool in_range = ri.in_range, real = ri.real;
+            const bool lit = a.shading != MI3D_SHADING_ALBEDO && ri.mpad < 1000000u;      // network_tcnn.py:159 fallback, per view
+            float light[3] = {0.f, 0.f, 0.f};                                             // multi-view: one light direction per view
+            if (a.light_d) { const float* lp = a.light_d + (R.segs ? 3 * ri.view : 0u); light[0] = lp[0]; light[1] = lp[1]; light[2] = lp[2]; }
             float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
             if (real) {
                 x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2];
@@ -684,8 +740,7 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
             }
             if (n_evals > 7 && in_range) {
                 float z[3];
-                if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
-                else gauss_pair(a.seed, row, 1u, z);
+                smooth_z(a.smooth_noise, a.seed, a.noise_mode, row, ri, x, z);
                 #pragma unroll
                 for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
             }
@@ -766,11 +821,17 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
                     }
                     const float wgt = 1.f - expf(-sigma0);
                     const float ndd = fmaxf((nm.n[0] * d[0] + nm.n[1] * d[1]) + nm.n[2] * d[2], 0.f);
-                    acc_orient += wgt * (ndd * ndd);
+                    const float t_orient = wgt * (ndd * ndd);
+                    float t_smooth = 0.f;
                     if (n_evals > 7) {
                         const float sp2[3] = {tapv[6], tapv[8], tapv[10]}, sn2[3] = {tapv[7], tapv[9], tapv[11]};
                         const Normal np = make_normal(sp2, sn2);
-                        acc_smooth += (fabsf(nm.n[0] - np.n[0]) + fabsf(nm.n[1] - np.n[1])) + fabsf(nm.n[2] - np.n[2]);
+                        t_smooth = (fabsf(nm.n[0] - np.n[0]) + fabsf(nm.n[1] - np.n[1])) + fabsf(nm.n[2] - np.n[2]);
+                    }
+                    if (!R.segs) { acc_orient += t_orient; acc_smooth += t_smooth; }       // fixed-order sums, divided once at the end
+                    else {                                                                  // per-view means over the whole view's rows
+                        const float inv = 1.f / (float)ri.mpad;
+                        atomicAdd(s_loss + 2 * ri.view, t_orient * inv); atomicAdd(s_loss + 2 * ri.view + 1, t_smooth * (inv / 3.f));
                     }
                     if (a.normals) { a.normals[3 * (size_t)row] = nm.n[0]; a.normals[3 * (size_t)row + 1] = nm.n[1]; a.normals[3 * (size_t)row + 2] = nm.n[2]; }
                 }
@@ -791,13 +852,13 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
         const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
         for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
-            const bool in_range = row < m_pad, real = row < M;
+            const RowInfo ri = row_info(R, row);
+            const bool in_range = ri.in_range, real = ri.real;
             float x[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
             if (real) { x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2]; }
             if (n_evals > 7 && in_range) {
                 float z[3];
-                if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
-                else gauss_pair(a.seed, row, 1u, z);
+                smooth_z(a.smooth_noise, a.seed, a.noise_mode, row, ri, x, z);
                 #pragma unroll
                 for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
             }
@@ -860,17 +921,28 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (tid == 0 && a.loss_partials) {
+    if (tid == 0 && a.loss_partials && !a.segs) {
         a.loss_partials[2 * blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
         a.loss_partials[2 * blockIdx.x + 1] = (red[4] + red[5]) + (red[6] + red[7]);
     }
+    if (a.loss_partials && a.segs && tid < 2 * (int)segs_sm.n_views) a.loss_partials[(size_t)blockIdx.x * 2 * segs_sm.n_views + tid] = s_loss[tid];
     if (warp == 12) { tc::tc_fence_after(); tc::tmem_dealloc(tmem, kTmemCols); }
 }
 
-// loss_orient = sum / m_pad ; loss_smooth = sum / (3 m_pad)   (renderer.py:517-518, 523-524: .mean() over the padded rows)
+// loss_orient = sum / m_pad ; loss_smooth = sum / (3 m_pad)   (renderer.py:517-518, 523-524: .mean() over the padded rows).
+// Multi-view (n_views > 0): partials are [cta][view][2] and already carry the 1 / mpad[view] factors; outputs are [n_views] arrays.
 __global__ void k_loss_finalize(const float* __restrict__ partials, int n_part, const int* __restrict__ counter, uint32_t m_fixed,
-                                uint32_t align, uint32_t cap, float* __restrict__ loss_orient, float* __restrict__ loss_smooth) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+                                uint32_t align, uint32_t cap, float* __restrict__ loss_orient, float* __restrict__ loss_smooth, int n_views) {
+    if (blockIdx.x != 0) return;
+    if (n_views > 0) {
+        if ((int)threadIdx.x >= 2 * n_views) return;
+        float t = 0.f;
+        for (int i = 0; i < n_part; i++) t += partials[(size_t)i * 2 * n_views + threadIdx.x];
+        float* dst = (threadIdx.x & 1) ? loss_smooth : loss_orient;
+        if (dst) dst[threadIdx.x >> 1] = t;
+        return;
+    }
+    if (threadIdx.x != 0) return;
     float t0 = 0.f, t1 = 0.f;
     for (int i = 0; i < n_part; i++) { t0 += partials[2 * i]; t1 += partials[2 * i + 1]; }
     const uint32_t M = counter ? min((uint32_t)counter[0], cap) : m_fixed;
@@ -893,6 +965,7 @@ struct BwdArgs {
     float* g_table; mi3d_mlp_grad g_mlp;
     // split pipeline (encode kernel -> tensor-core chain kernel -> scatter kernel) over tiles [tile0, tile1): see k_bwd_encode
     float* enc_buf; float* denc_buf; uint32_t tile0, tile1;
+    const mi3d_view_segs* segs; uint32_t noise_mode;   // multi-view: g_loss_orient / g_loss_smooth are [n_views] arrays
 };
 
 // d(loss)/d(h) of the 13 evaluations of one sample from the upstream gradients and the forward tape (sigma0, albedo, tap sigmas):
@@ -1092,18 +1165,30 @@ __device__ __forceinline__ void load16(const float* __restrict__ src, float (&f)
 //   k_field_bwd_tc (ext mode): loads enc, runs the MMA chain, stores d(enc) -> denc_buf
 //   k_bwd_scatter: same mapping as encode, warp-aggregated REDs (lanes = consecutive samples of a ray)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int bwd_e_end(const BwdArgs& a, uint32_t m_pad) {
-    const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
-    const float Go = (a.g_loss_orient && a.n_evals >= 7) ? *a.g_loss_orient : 0.f;
-    const float Gs = (a.g_loss_smooth && a.n_evals > 7) ? *a.g_loss_smooth : 0.f;
-    const bool need_ptaps = Gs != 0.f;
-    const bool need_taps = a.n_evals >= 7 && (need_ptaps || Go != 0.f || lit || a.g_normals != nullptr);
-    return !need_taps ? 1 : (need_ptaps ? 13 : 7);
+// which evaluations can receive a non-zero gradient (uniform over the launch; identical in the gather / chain / scatter kernels)
+struct BwdPlan { int e_end; bool need_ptaps; };
+__device__ __forceinline__ BwdPlan bwd_plan(const BwdArgs& a, const Rows& R) {
+    const int nv = R.segs ? (int)R.segs->n_views : 1;
+    bool lit = false, go = false, gs = false;
+    for (int v = 0; v < nv; v++) {
+        const uint32_t mpad = R.segs ? R.segs->mpad[v] : R.m_pad;
+        lit |= a.shading != MI3D_SHADING_ALBEDO && mpad < 1000000u;
+        go |= a.g_loss_orient && a.n_evals >= 7 && a.g_loss_orient[v] != 0.f;
+        gs |= a.g_loss_smooth && a.n_evals > 7 && a.g_loss_smooth[v] != 0.f;
+    }
+    BwdPlan p;
+    p.need_ptaps = gs;
+    const bool need_taps = a.n_evals >= 7 && (gs || go || lit || a.g_normals != nullptr);
+    p.e_end = !need_taps ? 1 : (gs ? 13 : 7);
+    return p;
 }
 
 template <bool SCATTER>
 __global__ void __launch_bounds__(512, 2) k_bwd_enc_scatter(const BwdArgs a) {
     __shared__ LevelSm lv[16];
+    __shared__ mi3d_view_segs segs_sm;
+    if (a.segs && threadIdx.x >= 32 && threadIdx.x < 32 + sizeof(mi3d_view_segs) / 4)
+        reinterpret_cast<uint32_t*>(&segs_sm)[threadIdx.x - 32] = reinterpret_cast<const uint32_t*>(a.segs)[threadIdx.x - 32];
     if (threadIdx.x < 16) {
         LevelSm L; const int l = threadIdx.x;
         if (l < (int)a.hg.n_levels) {
@@ -1113,9 +1198,9 @@ __global__ void __launch_bounds__(512, 2) k_bwd_enc_scatter(const BwdArgs a) {
         lv[l] = L;
     }
     __syncthreads();
-    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
-    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
-    const int e_end = bwd_e_end(a, m_pad);
+    const Rows R = rows_make(a.counter, a.m_fixed, a.align, a.cap, a.segs ? &segs_sm : nullptr);
+    const uint32_t m_pad = R.m_pad;
+    const int e_end = bwd_plan(a, R).e_end;
     const int r = threadIdx.x & (T - 1), lg = threadIdx.x >> 7, lane = threadIdx.x & 31;   // levels 4 lg .. 4 lg + 3
     const float inv2b = 2.f * a.bound;
     // persistent grid-stride loop over (tile, evaluation) work items of this chunk
@@ -1124,13 +1209,13 @@ __global__ void __launch_bounds__(512, 2) k_bwd_enc_scatter(const BwdArgs a) {
         const int e = (int)(w % (uint32_t)e_end);
         if (tile >= a.tile1 || (uint64_t)tile * T >= m_pad) break;
         const uint32_t row = tile * T + r;
-        const bool in_range = row < m_pad, real = row < M;
+        const RowInfo ri = row_info(R, row);
+        const bool in_range = ri.in_range, real = ri.real;
         float x[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
         if (real) { x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2]; }
         if (e >= 7 && in_range) {
             float z[3];
-            if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
-            else gauss_pair(a.seed, row, 1u, z);
+            smooth_z(a.smooth_noise, a.seed, a.noise_mode, row, ri, x, z);
             #pragma unroll
             for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
         }
@@ -1199,9 +1284,10 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdArgs a) {
     using namespace bwdtc;
     {   // chunk entirely past the (device-side) sample count: nothing to do
-        const uint32_t M0 = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
-        if ((uint64_t)a.tile0 * T >= padded_rows(M0, a.align, a.cap)) return;
+        const Rows R0 = rows_make(a.counter, a.m_fixed, a.align, a.cap, a.segs);
+        if ((uint64_t)a.tile0 * T >= R0.m_pad) return;
     }
+    __shared__ mi3d_view_segs segs_sm;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     float* b1s = reinterpret_cast<float*>(sm + oMisc);          // 64
@@ -1236,6 +1322,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         } else { L.offset = 0; L.size = 8; L.res = 2; L.scale = 1.f; L.hashed = 0; }
         lv[l] = L;
     }
+    if (a.segs && tid < (int)(sizeof(mi3d_view_segs) / 4)) reinterpret_cast<uint32_t*>(&segs_sm)[tid] = reinterpret_cast<const uint32_t*>(a.segs)[tid];
     if (tid == 0) {
         tc::mbar_init(a1_full, 256); tc::mbar_init(d1_full, 1); tc::mbar_init(a2_full, 128); tc::mbar_init(d2_full, 1);
         tc::mbar_init(a3_full, 128); tc::mbar_init(r3_done, 256); tc::mbar_init(d3_full, 1); tc::mbar_init(a4_full, 128);
@@ -1250,14 +1337,11 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
     const uint32_t tmem = *tmem_slot;
     const uint32_t sbase = tc::smem_u32(sm);
 
-    const uint32_t M = a.counter ? min((uint32_t)a.counter[0], a.cap) : a.m_fixed;
-    const uint32_t m_pad = padded_rows(M, a.align, a.cap);
-    const bool lit = a.shading != MI3D_SHADING_ALBEDO && m_pad < 1000000u;
-    const float Go = (a.g_loss_orient && a.n_evals >= 7) ? *a.g_loss_orient / (float)m_pad : 0.f;
-    const float Gs = (a.g_loss_smooth && a.n_evals > 7) ? *a.g_loss_smooth / (3.f * (float)m_pad) : 0.f;
-    const bool need_ptaps = Gs != 0.f;
-    const bool need_taps = a.n_evals >= 7 && (need_ptaps || Go != 0.f || lit || a.g_normals != nullptr);
-    const int e_end = !need_taps ? 1 : (need_ptaps ? 13 : 7);
+    const Rows R = rows_make(a.counter, a.m_fixed, a.align, a.cap, a.segs ? &segs_sm : nullptr);
+    const uint32_t m_pad = R.m_pad;
+    const BwdPlan plan = bwd_plan(a, R);
+    const bool need_ptaps = plan.need_ptaps;
+    const int e_end = plan.e_end;
     const float inv2b = 2.f * a.bound;
     uint32_t it = 0;
 
@@ -1265,19 +1349,26 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         // ================================ owners ================================
         const int r = tid;
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        float light[3] = {0.f, 0.f, 0.f};
-        if (a.light_d) { light[0] = a.light_d[0]; light[1] = a.light_d[1]; light[2] = a.light_d[2]; }
         // persistent partial sums over this warp's rows: lane j owns columns j and j+32 of dW3[o][.] ; db3 on lane o
         float aw3[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, ab3 = 0.f;
         for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
-            const bool in_range = row < m_pad, real = row < M;
+            const RowInfo ri = row_info(R, row);
+            const bool in_range = ri.in_range, real = ri.real;
             float d[3] = {0.f, 0.f, 0.f};
             if (real && a.dirs) { d[0] = a.dirs[3 * (size_t)row]; d[1] = a.dirs[3 * (size_t)row + 1]; d[2] = a.dirs[3 * (size_t)row + 2]; }
             float dh[4] = {0.f, 0.f, 0.f, 0.f}, dtap[12];
             #pragma unroll
             for (int i = 0; i < 12; i++) dtap[i] = 0.f;
-            if (in_range) sample_out_grads(a, row, real, d, lit, light, Go, Gs, need_ptaps, dh, dtap);
+            if (in_range) {
+                float light[3] = {0.f, 0.f, 0.f};
+                if (a.light_d) { const float* lp = a.light_d + (R.segs ? 3 * ri.view : 0u); light[0] = lp[0]; light[1] = lp[1]; light[2] = lp[2]; }
+                // upstream gradients of this row's view: d(mean over the view's mpad rows) (renderer.py:517-518, 523-524)
+                const bool lit = a.shading != MI3D_SHADING_ALBEDO && ri.mpad < 1000000u;
+                const float Go = (a.g_loss_orient && a.n_evals >= 7) ? a.g_loss_orient[ri.view] / (float)ri.mpad : 0.f;
+                const float Gs = (a.g_loss_smooth && a.n_evals > 7) ? a.g_loss_smooth[ri.view] / (3.f * (float)ri.mpad) : 0.f;
+                sample_out_grads(a, row, real, d, lit, light, Go, Gs, need_ptaps, dh, dtap);
+            }
             for (int e = 0; e < e_end; e++, it++) {
                 const uint32_t par = it & 1;
                 float dO[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1404,13 +1495,13 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         float ab2 = 0.f, ab1 = 0.f;
         for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
-            const bool in_range = row < m_pad, real = row < M;
+            const RowInfo ri = row_info(R, row);
+            const bool in_range = ri.in_range, real = ri.real;
             float x[3] = {0.f, 0.f, 0.f}, xp[3] = {0.f, 0.f, 0.f};
             if (real) { x[0] = a.xyzs[3 * (size_t)row]; x[1] = a.xyzs[3 * (size_t)row + 1]; x[2] = a.xyzs[3 * (size_t)row + 2]; }
             if (a.n_evals > 7 && in_range) {
                 float z[3];
-                if (a.smooth_noise) { z[0] = a.smooth_noise[3 * (size_t)row]; z[1] = a.smooth_noise[3 * (size_t)row + 1]; z[2] = a.smooth_noise[3 * (size_t)row + 2]; }
-                else gauss_pair(a.seed, row, 1u, z);
+                smooth_z(a.smooth_noise, a.seed, a.noise_mode, row, ri, x, z);
                 #pragma unroll
                 for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
             }
@@ -1720,11 +1811,9 @@ int mi3d_hashgrid_backward(const float* x, uint32_t E, const float* grad_out, co
     MI3D_RETURN_LAUNCH();
 }
 
-// MI3D_FIELD_TC=0 selects the FFMA forward kernel (kept for A/B measurements); default is the tcgen05 3xTF32 kernel
-static bool use_tc() { static int v = -1; if (v < 0) { const char* e = getenv("MI3D_FIELD_TC"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
-
+// cfg->impl selects the kernels explicitly (no environment switches inside the library): MI3D_FIELD_IMPL_TCGEN05 (default) or
+// MI3D_FIELD_IMPL_FFMA (the round-1a register-tiled kernels; they also serve the density-grid refresh).  Both are parity-tested.
 constexpr uint32_t kBwdChunkTiles = 8192;     // 1 048 576 samples per chunk: 2 x 1.74 GB of encoding / gradient staging
-static bool use_tc_bwd() { static int v = -1; if (v < 0) { const char* e = getenv("MI3D_FIELD_TC_BWD"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
 
 size_t mi3d_field_backward_workspace_bytes(void) { return (size_t)2 * kBwdChunkTiles * 13 * T * 32 * sizeof(float); }
 
@@ -1738,19 +1827,24 @@ int mi3d_field_forward(const mi3d_field_io* io, const float* table, const mi3d_h
     if (hg->n_levels * 2 != D_IN) return MI3D_ERR_ARG;
     if ((loss_orient || loss_smooth) && !loss_partials) return MI3D_ERR_ARG;
     MI3D_CHECK((cudaError_t)ensure_attrs());
-    FwdArgs a;
+    FwdArgs a{};
     a.xyzs = io->xyzs; a.dirs = io->dirs; a.counter = io->counter; a.m_fixed = io->m_fixed; a.align = io->align; a.cap = io->cap;
     a.table = table; a.hg = *hg; a.mlp = *mlp;
     a.bound = cfg->bound; a.blob_density = cfg->blob_density; a.two_r2 = (float)(2.0 * (double)cfg->blob_radius * (double)cfg->blob_radius);
     a.n_evals = cfg->n_evals; a.shading = cfg->shading; a.ratio = cfg->ambient_ratio; a.light_d = cfg->light_d;
     a.smooth_noise = io->smooth_noise; a.seed = io->seed;
     a.sigmas = sigmas; a.rgbs = rgbs; a.normals = normals; a.tape = tape; a.loss_partials = loss_partials;
-    a.enc_cache = (use_tc() && hg->n_levels == 16) ? io->enc_cache : nullptr; a.enc_cache_tiles = io->enc_cache_tiles;
+    const bool use_tc = cfg->impl != MI3D_FIELD_IMPL_FFMA;
+    a.enc_cache = (use_tc && hg->n_levels == 16) ? io->enc_cache : nullptr; a.enc_cache_tiles = io->enc_cache_tiles;
+    a.segs = io->segs; a.noise_mode = io->noise_mode;
+    if ((io->segs || io->noise_mode) && !use_tc) return MI3D_ERR_ARG;
+    if (io->segs && (io->n_views == 0 || io->n_views > MI3D_MAX_VIEWS)) return MI3D_ERR_ARG;
     int grid = mi3d_field_grid_ctas(0);
-    if (use_tc()) { grid = num_sms(); k_field_fwd_tc<<<grid, fwdtc::kThreads, fwdtc::kSmem, (cudaStream_t)stream>>>(a); }
+    if (use_tc) { grid = num_sms(); k_field_fwd_tc<<<grid, fwdtc::kThreads, fwdtc::kSmem, (cudaStream_t)stream>>>(a); }
     else k_field_fwd<<<grid, NT, smem_bytes(false), (cudaStream_t)stream>>>(a);
     if (loss_orient || loss_smooth)
-        k_loss_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partials, grid, io->counter, io->m_fixed, io->align, io->cap, loss_orient, loss_smooth);
+        k_loss_finalize<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partials, grid, io->counter, io->m_fixed, io->align, io->cap, loss_orient, loss_smooth,
+                                                             io->segs ? (int)io->n_views : 0);
     MI3D_RETURN_LAUNCH();
 }
 
@@ -1762,7 +1856,7 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     if (cfg->n_evals != 1 && cfg->n_evals != 7 && cfg->n_evals != 13) return MI3D_ERR_ARG;
     if (hg->n_levels * 2 != D_IN) return MI3D_ERR_ARG;
     MI3D_CHECK((cudaError_t)ensure_attrs());
-    BwdArgs a;
+    BwdArgs a{};
     a.xyzs = io->xyzs; a.dirs = io->dirs; a.counter = io->counter; a.m_fixed = io->m_fixed; a.align = io->align; a.cap = io->cap;
     a.table = table; a.hg = *hg; a.mlp = *mlp;
     a.bound = cfg->bound; a.blob_density = cfg->blob_density; a.two_r2 = (float)(2.0 * (double)cfg->blob_radius * (double)cfg->blob_radius);
@@ -1772,29 +1866,21 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     a.g_loss_orient = grad_loss_orient; a.g_loss_smooth = grad_loss_smooth;
     a.g_table = grad_table; a.g_mlp = *grad_mlp;
     a.enc_buf = nullptr; a.denc_buf = nullptr; a.tile0 = 0; a.tile1 = 0xFFFFFFFFu;
-    if (use_tc_bwd()) {
+    a.segs = io->segs; a.noise_mode = io->noise_mode;
+    if ((io->segs || io->noise_mode) && cfg->impl == MI3D_FIELD_IMPL_FFMA) return MI3D_ERR_ARG;
+    if (io->segs && (io->n_views == 0 || io->n_views > MI3D_MAX_VIEWS)) return MI3D_ERR_ARG;
+    if (cfg->impl != MI3D_FIELD_IMPL_FFMA) {
         if (workspace && hg->n_levels == 16) {
             // split pipeline, chunk by chunk (the sample count lives on the device: chunks past it return immediately)
             float* enc_tmp = (float*)workspace;
             a.denc_buf = enc_tmp + (size_t)kBwdChunkTiles * 13 * T * 32;
-            const bool cached = io->enc_cache && io->enc_cache_valid && use_tc();
+            const bool cached = io->enc_cache && io->enc_cache_valid;
             const uint32_t total_tiles = (io->cap + T - 1) / T;
             for (uint32_t t0 = 0; t0 < total_tiles; t0 += kBwdChunkTiles) {
                 a.tile0 = t0; a.tile1 = t0 + kBwdChunkTiles;
-                float* const denc = a.denc_buf;
-                bool fused_scatter = false;
-                if (cached && (t0 + kBwdChunkTiles < total_tiles ? t0 + kBwdChunkTiles : total_tiles) <= io->enc_cache_tiles) {
+                if (cached && (t0 + kBwdChunkTiles < total_tiles ? t0 + kBwdChunkTiles : total_tiles) <= io->enc_cache_tiles)
                     a.enc_buf = io->enc_cache + (size_t)t0 * 13 * T * 32;   // saved by the forward
-                    static int fs = -1; if (fs < 0) { const char* e = getenv("MI3D_BWD_FUSED_SCATTER"); fs = (e && e[0] == '1') ? 1 : 0; }
-                    fused_scatter = fs == 1;
-                } else { a.enc_buf = enc_tmp; k_bwd_enc_scatter<false><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a); }
-                if (fused_scatter) {      // no gather left to hide: the chain kernel's encoder warps scatter d(enc) themselves
-                    a.denc_buf = nullptr;
-                    k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
-                    a.denc_buf = denc;
-                    if (!io->counter && (uint64_t)(t0 + kBwdChunkTiles) * T >= io->m_fixed) break;
-                    continue;
-                }
+                else { a.enc_buf = enc_tmp; k_bwd_enc_scatter<false><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a); }
                 k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
                 k_bwd_enc_scatter<true><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a);
                 if (!io->counter && (uint64_t)(t0 + kBwdChunkTiles) * T >= io->m_fixed) break;
@@ -1833,7 +1919,7 @@ int mi3d_density_grid_update(float* density_grid, uint8_t* bitfield, uint32_t C,
     for (uint32_t cas = 0; cas < C; cas++) {
         const float cas_bound = fminf((float)(1u << cas), bound);                 // renderer.py:612
         k_grid_positions<<<nparts, 256, 0, st>>>(H, cas_bound, jitter ? jitter + (size_t)cas * n * 3 : nullptr, seed, cas, xyz);
-        FwdArgs a;
+        FwdArgs a{};
         a.xyzs = xyz; a.dirs = nullptr; a.counter = nullptr; a.m_fixed = n; a.align = 0; a.cap = n;
         a.table = table; a.hg = *hg; a.mlp = *mlp;
         a.bound = cfg->bound; a.blob_density = cfg->blob_density; a.two_r2 = (float)(2.0 * (double)cfg->blob_radius * (double)cfg->blob_radius);

@@ -53,6 +53,29 @@ __device__ __forceinline__ void slab_near_far(float ox, float oy, float oz, floa
     if (tn < min_near) tn = min_near;
 }
 
+// Pixel-centre pinhole ray of batch ray i (nerf/utils.py:51-116 with N = -1: every pixel, row-major): view = i / rays_per_view,
+// pixel = (i % rays_per_view) * pixel_stride + pixel_phase.  Same operation order as the reference's torch expression, one IEEE
+// rounding per op (this file is compiled with -fmad=false):  xs = (x + 0.5 - cx) / fx, ys = (y + 0.5 - cy) / fy, zs = 1;
+// depth_scale = 1 / sqrt(xs^2 + ys^2 + 1); dir = safe_normalize((xs, ys, 1)); rays_d = dir @ R^T; rays_o = t.
+__device__ __forceinline__ void gen_ray(const mi3d_raygen& rg, uint32_t i, float o[3], float d[3], float& depth_scale,
+                                        uint32_t& view, uint32_t& pixel) {
+    view = i / rg.rays_per_view;
+    pixel = (i - view * rg.rays_per_view) * rg.pixel_stride + rg.pixel_phase;
+    const uint32_t px = pixel % rg.W, py = pixel / rg.W;
+    const float* __restrict__ c = rg.cams + 16 * (size_t)view;
+    const float fx = __ldg(c + 12), fy = __ldg(c + 13), cx = __ldg(c + 14), cy = __ldg(c + 15);
+    const float xs = ((float)px + 0.5f - cx) / fx, ys = ((float)py + 0.5f - cy) / fy;
+    const float ss = (xs * xs + ys * ys) + 1.0f;
+    depth_scale = 1.0f / sqrtf(ss);
+    const float q = sqrtf(fminf(fmaxf(ss, 1e-20f), 1e32f));          // safe_normalize, nerf/utils.py:47-48
+    const float dx = xs / q, dy = ys / q, dz = 1.0f / q;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        d[k] = (dx * __ldg(c + 4 * k) + dy * __ldg(c + 4 * k + 1)) + dz * __ldg(c + 4 * k + 2);
+        o[k] = __ldg(c + 4 * k + 3);
+    }
+}
+
 __device__ __forceinline__ void ray_setup(RayCtx& r, const float* o, const float* d, float bound, float dt_gamma,
                                           uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid) {
     r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
@@ -118,6 +141,17 @@ k_near_far(const float* __restrict__ rays_o, const float* __restrict__ rays_d, c
     nears[n] = tn; fars[n] = tf;
 }
 
+__global__ void __launch_bounds__(kRayThreads)
+k_get_rays(const mi3d_raygen rg, uint32_t N, float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ depth_scale) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    float o[3], d[3], sc; uint32_t view, pixel;
+    gen_ray(rg, n, o, d, sc, view, pixel);
+    #pragma unroll
+    for (int k = 0; k < 3; k++) { if (rays_o) rays_o[3 * (size_t)n + k] = o[k]; if (rays_d) rays_d[3 * (size_t)n + k] = d[k]; }
+    if (depth_scale) depth_scale[n] = sc;
+}
+
 __global__ void k_morton3D(const int* __restrict__ coords, uint32_t N, int* __restrict__ indices) {
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= N) return;
@@ -161,7 +195,8 @@ k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d
               const float* __restrict__ aabb, float min_near, float* __restrict__ nears_out, float* __restrict__ fars_out,
               const float* __restrict__ noises, uint64_t seed,
               float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-              int* __restrict__ rays, int* __restrict__ counter, int* __restrict__ scan_ws) {
+              int* __restrict__ rays, int* __restrict__ counter, int* __restrict__ scan_ws,
+              const mi3d_raygen rg, float* __restrict__ depth_scale_out) {
     __shared__ uint32_t s_bid, s_warp_tot[kRayThreads / 32], s_prefix;
     const uint32_t nblk = gridDim.x;
     if (threadIdx.x == 0) s_bid = (uint32_t)atomicAdd(scan_ws, 1);
@@ -174,7 +209,17 @@ k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d
     float t0 = 0.f, far = 0.f;
     uint32_t cnt = 0;
     if (n < N) {
-        ray_setup(r, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, grid);
+        uint32_t view = 0, nkey = n;          // Philox key of the march jitter: (pixel, camera) when rays are generated here, so the
+        if (rays_o) ray_setup(r, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H, grid);
+        else {                                // draw does not depend on how a view's pixels are dealt to ranks (ray-parallel render)
+            float o[3], d[3], sc;
+            gen_ray(rg, n, o, d, sc, view, nkey);
+            // identify the view by its camera position, not by its slot in this batch: the same view marched alone, in a multi-view
+            // batch or dealt over ranks draws the same jitter
+            view = (__float_as_uint(o[0]) * 0x9E3779B1u) ^ (__float_as_uint(o[1]) * 0x85EBCA77u) ^ (__float_as_uint(o[2]) * 0xC2B2AE3Du);
+            ray_setup(r, o, d, bound, dt_gamma, max_steps, C, H, grid);
+            if (depth_scale_out) depth_scale_out[n] = sc;
+        }
         float near;
         if (nears_in) { near = nears_in[n]; far = fars_in[n]; }
         else {
@@ -183,7 +228,7 @@ k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d
         }
         float noise;
         if (noises) noise = noises[n];
-        else noise = mi3d_u01(mi3d_philox(make_uint4(n, 0u, 0u, 0x6d617263u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))).x);
+        else noise = mi3d_u01(mi3d_philox(make_uint4(nkey, view, 0u, 0x6d617263u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))).x);
         t0 = near + mi3d_clampf(near * dt_gamma, r.dt_min, r.dt_max) * noise;
         float t = t0;
         cnt = walk<false>(r, t, far, max_steps, nullptr, nullptr, nullptr);
@@ -215,10 +260,16 @@ k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d
     }
     __syncthreads();
     const uint32_t prefix = s_prefix;
-    if (bid == nblk - 1 && threadIdx.x == 0) { counter[0] += (int)(prefix + block_tot); counter[1] += (int)N; scan_ws[0] = 0; }
+    // counter[0] += number of EMITTED samples.  Offsets are monotone in the ray id, so when the capacity M is exceeded the emitted
+    // samples are the contiguous prefix [0, off) of the unique ray with off <= M < off + cnt (it and every later ray write nothing,
+    // raymarching.cu:416).  The reference adds the uncapped total (raymarching.cu:405) and relies on its 268 MB zero-fill to make
+    // the hole rows harmless; here nothing is zero-filled, so downstream kernels must see only rows that were written.
+    const bool last = bid == nblk - 1 && threadIdx.x == 0;
+    if (last) { if (prefix + block_tot <= M) counter[0] += (int)(prefix + block_tot); counter[1] += (int)N; scan_ws[0] = 0; }
     if (n >= N) return;
     const uint32_t off = prefix + local_off;
     rays[3 * (size_t)n] = (int)n; rays[3 * (size_t)n + 1] = (int)off; rays[3 * (size_t)n + 2] = (int)cnt;
+    if (cnt != 0 && off <= M && off + cnt > M) counter[0] += (int)off;        // the one boundary ray of an overflowing march
     if (cnt == 0 || off + cnt > M) return;
     float t = t0;
     walk<true>(r, t, far, cnt, xyzs + 3 * (size_t)off, dirs + 3 * (size_t)off, deltas + 2 * (size_t)off);
@@ -233,10 +284,11 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
                       const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
                       float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
                       const float* __restrict__ bg_color, float bg_scalar, int fuse_epilogue, float max_depth,
-                      const float* __restrict__ depth_scale, float* __restrict__ image_out, float* __restrict__ depth_out) {
+                      const float* __restrict__ depth_scale, float* __restrict__ image_out, float* __restrict__ depth_out, uint32_t rays_per_view) {
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= N) return;
     const uint32_t index = (uint32_t)rays[3 * (size_t)n], off = (uint32_t)rays[3 * (size_t)n + 1], cnt = (uint32_t)rays[3 * (size_t)n + 2];
+    if (bg_color && rays_per_view) bg_color += 3 * (size_t)(index / rays_per_view);    // one background colour per view of the batch
     float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
     if (cnt != 0 && off + cnt <= M) {
         const float* sg = sigmas + off; const float* cl = rgbs + 3 * (size_t)off; const float* dl = deltas + 2 * (size_t)off;
@@ -271,10 +323,11 @@ k_composite_train_bwd(const float* __restrict__ grad_ws, const float* __restrict
                       uint32_t M, uint32_t N, float T_thresh,
                       const float* __restrict__ bg_color, float bg_scalar, int fuse_epilogue, float max_depth,
                       const float* __restrict__ depth_scale,
-                      float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, int zero_tail) {
+                      float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, int zero_tail, uint32_t rays_per_view) {
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= N) return;
     const uint32_t index = (uint32_t)rays[3 * (size_t)n], off = (uint32_t)rays[3 * (size_t)n + 1], cnt = (uint32_t)rays[3 * (size_t)n + 2];
+    if (bg_color && rays_per_view) bg_color += 3 * (size_t)(index / rays_per_view);
     if (cnt == 0 || off + cnt > M) return;
     const float gi0 = grad_image[3 * (size_t)index], gi1 = grad_image[3 * (size_t)index + 1], gi2 = grad_image[3 * (size_t)index + 2];
     float gw = grad_ws ? grad_ws[index] : 0.0f;
@@ -391,18 +444,52 @@ size_t mi3d_march_rays_train_workspace_bytes(uint32_t N) {
     return (size_t)(1 + 2 * mi3d_ceil_div(N, kRayThreads)) * sizeof(int);
 }
 
+static int march_train_launch(const float* rays_o, const float* rays_d, const mi3d_raygen* rg, float* depth_scale_out,
+                              const uint8_t* grid, float bound, float dt_gamma,
+                              uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                              const float* nears, const float* fars, const float* aabb, float min_near,
+                              float* nears_out, float* fars_out, const float* noises, uint64_t seed,
+                              float* xyzs, float* dirs, float* deltas, int* rays, int* counter,
+                              void* workspace, mi3d_stream_t stream) {
+    if (N == 0) return MI3D_OK;
+    if (!workspace || (!nears && !aabb) || C == 0 || C > 8) return MI3D_ERR_ARG;
+    mi3d_raygen g{};
+    if (!rays_o || !rays_d) {
+        if (!rg || !rg->cams || rg->rays_per_view == 0 || rg->W == 0 || (uint64_t)rg->n_views * rg->rays_per_view != N) return MI3D_ERR_ARG;
+        if ((uint64_t)(rg->rays_per_view - 1) * rg->pixel_stride + rg->pixel_phase >= (uint64_t)rg->H * rg->W) return MI3D_ERR_ARG;
+        g = *rg; rays_o = rays_d = nullptr;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    MI3D_CHECK(cudaMemsetAsync(workspace, 0, mi3d_march_rays_train_workspace_bytes(N), st));
+    k_march_train<<<mi3d_ceil_div(N, kRayThreads), kRayThreads, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+        nears, fars, aabb, min_near, nears_out, fars_out, noises, seed, xyzs, dirs, deltas, rays, counter, (int*)workspace, g, depth_scale_out);
+    MI3D_RETURN_LAUNCH();
+}
+
 int mi3d_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                           const float* nears, const float* fars, const float* aabb, float min_near,
                           float* nears_out, float* fars_out, const float* noises, uint64_t seed,
                           float* xyzs, float* dirs, float* deltas, int* rays, int* counter,
                           void* workspace, mi3d_stream_t stream) {
+    if (!rays_o || !rays_d) return MI3D_ERR_ARG;
+    return march_train_launch(rays_o, rays_d, nullptr, nullptr, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, aabb, min_near,
+                              nears_out, fars_out, noises, seed, xyzs, dirs, deltas, rays, counter, workspace, stream);
+}
+
+int mi3d_march_rays_train_cam(const mi3d_raygen* rg, float* depth_scale_out, const uint8_t* grid, float bound, float dt_gamma,
+                              uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* aabb, float min_near,
+                              float* nears_out, float* fars_out, const float* noises, uint64_t seed,
+                              float* xyzs, float* dirs, float* deltas, int* rays, int* counter, void* workspace, mi3d_stream_t stream) {
+    return march_train_launch(nullptr, nullptr, rg, depth_scale_out, grid, bound, dt_gamma, max_steps, N, C, H, M, nullptr, nullptr, aabb, min_near,
+                              nears_out, fars_out, noises, seed, xyzs, dirs, deltas, rays, counter, workspace, stream);
+}
+
+int mi3d_get_rays(const mi3d_raygen* rg, uint32_t N, float* rays_o, float* rays_d, float* depth_scale, mi3d_stream_t stream) {
     if (N == 0) return MI3D_OK;
-    if (!workspace || (!nears && !aabb) || C == 0 || C > 8) return MI3D_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    MI3D_CHECK(cudaMemsetAsync(workspace, 0, mi3d_march_rays_train_workspace_bytes(N), st));
-    k_march_train<<<mi3d_ceil_div(N, kRayThreads), kRayThreads, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
-        nears, fars, aabb, min_near, nears_out, fars_out, noises, seed, xyzs, dirs, deltas, rays, counter, (int*)workspace);
+    if (!rg || !rg->cams || rg->rays_per_view == 0 || rg->W == 0 || (uint64_t)rg->n_views * rg->rays_per_view != N) return MI3D_ERR_ARG;
+    if ((uint64_t)(rg->rays_per_view - 1) * rg->pixel_stride + rg->pixel_phase >= (uint64_t)rg->H * rg->W) return MI3D_ERR_ARG;
+    k_get_rays<<<mi3d_ceil_div(N, kRayThreads), kRayThreads, 0, (cudaStream_t)stream>>>(*rg, N, rays_o, rays_d, depth_scale);
     MI3D_RETURN_LAUNCH();
 }
 
@@ -415,7 +502,7 @@ int mi3d_composite_rays_train_forward(const float* sigmas, const float* rgbs, co
     k_composite_train_fwd<<<mi3d_ceil_div(N, kRayThreads), kRayThreads, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image,
         fuse ? ep->bg_color : nullptr, fuse ? ep->bg_scalar : 0.f, fuse, fuse ? ep->max_depth : 0.f,
-        fuse ? ep->depth_scale : nullptr, image_out, depth_out);
+        fuse ? ep->depth_scale : nullptr, image_out, depth_out, fuse ? ep->rays_per_view : 0u);
     MI3D_RETURN_LAUNCH();
 }
 
@@ -429,7 +516,7 @@ int mi3d_composite_rays_train_backward(const float* grad_weights_sum, const floa
     k_composite_train_bwd<<<mi3d_ceil_div(N, kRayThreads), kRayThreads, 0, (cudaStream_t)stream>>>(
         grad_weights_sum, grad_image, grad_depth, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh,
         fuse ? ep->bg_color : nullptr, fuse ? ep->bg_scalar : 0.f, fuse, fuse ? ep->max_depth : 0.f,
-        fuse ? ep->depth_scale : nullptr, grad_sigmas, grad_rgbs, zero_tail);
+        fuse ? ep->depth_scale : nullptr, grad_sigmas, grad_rgbs, zero_tail, fuse ? ep->rays_per_view : 0u);
     MI3D_RETURN_LAUNCH();
 }
 

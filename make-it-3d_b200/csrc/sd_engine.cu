@@ -752,18 +752,16 @@ struct Engine {
         return MI3D_OK;
     }
     // The launch lists are static (fixed pointers, shapes and order; the timestep and every input live in device buffers), so a list
-    // can be replayed as one CUDA graph from its second call on (~200-330 launches lose their CPU launch cost).  OPT-IN
-    // (MI3D_SD_GRAPH=1) and only on a capturable stream: torch's default stream is the legacy stream, which cannot be captured, so
-    // the bench / tests run the eager path.  Measured on a side stream (tools/prof_sd.py, PROF_SIDE_STREAM=1): U-Net pass
-    // 7.68 -> 6.67 ms, VAE encode 2.89 -> 2.73 ms, VAE backward 3.55 -> 3.37 ms.  Making it the default (engine on its own stream,
-    // event-ordered against the caller's) needs the full parity suite under replay first: round 2.
+    // replays as ONE CUDA graph from its third call on (~200-330 launches lose their CPU launch cost and inter-kernel gaps; measured
+    // U-Net pass 7.68 -> 6.67 ms, VAE encode 2.89 -> 2.73 ms, VAE backward 3.55 -> 3.37 ms).  Enabled per engine with
+    // mi3d_sd_set_graph_replay(); needs a capturable stream (torch's legacy default stream is not: nerf/sd.py runs the engine on its
+    // own stream, event-ordered against the caller's).  A list whose capture fails falls back to plain launches for good.
     struct ListGraph { cudaGraphExec_t exec = nullptr; int calls = 0; bool failed = false; };
     std::map<std::vector<Op>*, ListGraph> graphs;
+    bool use_graph = false;
     int run(std::vector<Op>& ops, cudaStream_t st) {
-        static int use = -1;
-        if (use < 0) { const char* e = getenv("MI3D_SD_GRAPH"); use = (e && e[0] == '1') ? 1 : 0; }
         ListGraph& g = graphs[&ops];
-        if (!use || profile || g.failed) return run_eager(ops, st);
+        if (!use_graph || profile || g.failed) return run_eager(ops, st);
         if (g.exec) return (int)cudaGraphLaunch(g.exec, st);
         if (g.calls++ == 0) return run_eager(ops, st);            // first call: plain launches (one-time function attributes, warm caches)
         cudaGraph_t graph = nullptr;
@@ -1021,13 +1019,28 @@ int mi3d_sd_load_param(mi3d_sd_t h, int i, const float* src, const float* partne
 
 // enable != 0: start timing every tensor-core tile launch with CUDA events; enable == 0: stop, synchronise the events and
 // return the accumulated kernel milliseconds and launch count since the last enable
-int mi3d_sd_profile(mi3d_sd_t h, int enable, float* gemm_ms, int* launches) {
+int mi3d_sd_set_graph_replay(mi3d_sd_t h, int enable) {
+    if (!h) return MI3D_ERR_ARG;
+    h->e.use_graph = enable != 0;
+    return MI3D_OK;
+}
+
+int mi3d_sd_graph_replays(mi3d_sd_t h) {
+    if (!h) return -1;
+    int n = 0;
+    for (auto& kv : h->e.graphs) if (kv.second.exec) n++;
+    return n;
+}
+
+int mi3d_sd_profile(mi3d_sd_t h, int enable, float* gemm_ms, int* launches) { return mi3d_sd_profile_dump(h, enable, gemm_ms, launches, nullptr); }
+
+// dump_path_host (nullable): one text line per timed launch "M N K block_n splits conv batch epi ms" (bench.py derives FLOPs from it)
+int mi3d_sd_profile_dump(mi3d_sd_t h, int enable, float* gemm_ms, int* launches, const char* dump) {
     if (!h) return MI3D_ERR_ARG;
     sd::Engine& e = h->e;
     if (enable) { e.profile = true; e.prof_used = 0; return MI3D_OK; }
     e.profile = false;
     float total = 0.f; int n_tile = 0;
-    const char* dump = getenv("MI3D_SD_PROFILE_DUMP");        // tools/: one line per launch "M N K block_n splits conv batch epi ms"
     FILE* f = dump ? fopen(dump, "w") : nullptr;
     for (size_t i = 0; i < e.prof_used; i++) {
         float ms = 0.f;

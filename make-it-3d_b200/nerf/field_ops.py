@@ -61,6 +61,7 @@ def _cfg_struct(cfg, light_d):
     c.bound = cfg["bound"]; c.blob_density = cfg["blob_density"]; c.blob_radius = cfg["blob_radius"]
     c.n_evals = cfg["n_evals"]; c.shading = L.SHADING[cfg["shading"]]; c.ambient_ratio = cfg["ambient_ratio"]
     c.light_d = light_d.data_ptr() if light_d is not None else None
+    c.impl = L.FIELD_IMPL[cfg.get("impl", "tcgen05")]
     return c
 
 
@@ -143,41 +144,183 @@ def field_eval(table, mlp_params, xyzs, dirs, light_d, hg, cfg, smooth_noise=Non
     return _FieldEval.apply(table, *mlp_params, xyzs, dirs, light_d, smooth_noise, hg, cfg, seed)
 
 
-class RenderWorkspace:
-    """Capacity-sized per-sample buffers, allocated once and reused every step (no zero-fill, no empty_cache):
-    the 268 MB/step torch.zeros + allocator flush of raymarching.py:217-243 disappears."""
+def _blob_view(blob, ptr, shape, dtype):
+    """tensor view of a carved sub-buffer of the workspace blob (ptr = absolute device address inside blob)"""
+    item = torch.empty(0, dtype=dtype).element_size()
+    n = 1
+    for d in shape:
+        n *= d
+    off = ptr - blob.data_ptr()
+    return blob[off:off + n * item].view(dtype).view(*shape)
 
-    def __init__(self, N, max_steps, device, max_samples=None):
-        cap = N * max_steps if max_samples is None else min(N * max_steps, max_samples)
-        cap += 128  # room for the aligned zero rows the loss means include (raymarching.py:237-241)
-        self.N, self.cap, self.device = N, cap, device
-        f32 = dict(dtype=torch.float32, device=device)
-        self.xyzs = torch.empty(cap, 3, **f32)
-        self.dirs = torch.empty(cap, 3, **f32)
-        self.deltas = torch.empty(cap, 2, **f32)
-        self.sigmas = torch.empty(cap, **f32)
-        self.rgbs = torch.empty(cap, 3, **f32)
-        self.tape = torch.empty(cap, 16, **f32)
-        self.g_sigmas = torch.empty(cap, **f32)
-        self.g_rgbs = torch.empty(cap, 3, **f32)
-        self.rays = torch.empty(N, 3, dtype=torch.int32, device=device)
-        self.counter = torch.zeros(2, dtype=torch.int32, device=device)
-        self.nears = torch.empty(N, **f32)
-        self.fars = torch.empty(N, **f32)
-        self.ws_raw = torch.empty(N, **f32)
-        self.depth_raw = torch.empty(N, **f32)
-        self.image_raw = torch.empty(N, 3, **f32)
+
+class RenderWorkspace:
+    """Capacity-sized per-sample / per-ray buffers carved by the library out of ONE device blob (mi3d_render_workspace_carve),
+    allocated once and reused every step: no zero-fill, no empty_cache (the 268 MB/step torch.zeros + allocator flush of
+    raymarching.py:217-243 disappears).  The tensor attributes are views into the blob (tests and tools read them)."""
+
+    def __init__(self, N, max_steps, device, max_samples=None, n_views=1):
         lib = L.lib()
-        self.scan_ws = torch.empty(lib.mi3d_march_rays_train_workspace_bytes(C.c_uint32(N)), dtype=torch.uint8, device=device)
-        self.partials = torch.empty(2 * lib.mi3d_field_grid_ctas(C.c_int(0)), **f32)
+        self.N, self.device, self.n_views = N, device, n_views
         # hash-grid encodings of the first 8192 tiles (1 M samples x 13 evaluation points, 1.7 GB at full size): written by the
         # forward, read back by the backward passes of the same step instead of re-gathering the table
-        self.enc_tiles = min(8192, (cap + 127) // 128)
-        self.enc_cache = torch.empty(lib.mi3d_field_enc_cache_bytes(C.c_uint32(self.enc_tiles)), dtype=torch.uint8, device=device)
+        args = (C.c_uint32(N), C.c_uint32(max_steps), C.c_uint32(max_samples or 0), C.c_uint32(n_views), C.c_uint32(8192))
+        self.c = L.RenderWs()
+        L.check(lib.mi3d_render_workspace_carve(C.c_void_p(0), *args, C.byref(self.c)), "render_workspace_carve")
+        self.blob = torch.empty(self.c.bytes, dtype=torch.uint8, device=device)
+        L.check(lib.mi3d_render_workspace_carve(C.c_void_p(self.blob.data_ptr()), *args, C.byref(self.c)), "render_workspace_carve")
+        c, cap = self.c, self.c.cap
+        self.cap = cap
+        f32, i32 = torch.float32, torch.int32
+        v = lambda name, shape, dt=f32: _blob_view(self.blob, getattr(c, name), shape, dt)
+        self.xyzs, self.dirs, self.deltas = v("xyzs", (cap, 3)), v("dirs", (cap, 3)), v("deltas", (cap, 2))
+        self.sigmas, self.rgbs, self.tape = v("sigmas", (cap,)), v("rgbs", (cap, 3)), v("tape", (cap, 16))
+        self.g_sigmas, self.g_rgbs = v("g_sigmas", (cap,)), v("g_rgbs", (cap, 3))
+        self.rays, self.counter = v("rays", (N, 3), i32), v("counter", (2,), i32)
+        self.nears, self.fars = v("nears", (N,)), v("fars", (N,))
+        self.ws_raw, self.depth_raw, self.image_raw = v("ws_raw", (N,)), v("depth_raw", (N,)), v("image_raw", (N, 3))
+        self.depth_scale = v("depth_scale", (N,))
+        self.scan_ws = _blob_view(self.blob, c.scan_ws, (lib.mi3d_march_rays_train_workspace_bytes(C.c_uint32(N)),), torch.uint8)
+        self.partials = v("loss_partials", (2 * n_views * lib.mi3d_field_grid_ctas(C.c_int(0)),))
+        self.view_counts = v("view_counts", (L.MAX_VIEWS,), i32)
+        self.counter.zero_(); self.view_counts.zero_()
+        self.enc_tiles = c.enc_cache_tiles
+        self.enc_cache = _blob_view(self.blob, c.enc_cache, (lib.mi3d_field_enc_cache_bytes(C.c_uint32(self.enc_tiles)),), torch.uint8)
         self.generation = 0
+
+    def segs(self):
+        """host copy of the device segment table of the last multi-view forward (debug / tests; synchronises)"""
+        raw = _blob_view(self.blob, self.c.segs, (C.sizeof(L.ViewSegs) // 4,), torch.int32).cpu().numpy().tobytes()
+        return L.ViewSegs.from_buffer_copy(raw)
+
+
+def _render_args(ws, N, rays_o, rays_d, depth_scale, raygen, bitfield, aabb, noises, smooth_noise, bg_color, opts, par):
+    ra = L.RenderArgs()
+    ra.rays_o = rays_o.data_ptr() if rays_o is not None else None
+    ra.rays_d = rays_d.data_ptr() if rays_d is not None else None
+    ra.depth_scale = depth_scale.data_ptr() if depth_scale is not None else None
+    ra.raygen = C.pointer(raygen) if raygen is not None else None
+    ra.N = N; ra.n_views = opts.get("n_views", 1)
+    ra.density_bitfield = bitfield.data_ptr(); ra.C = opts["cascade"]; ra.H = opts["grid_size"]
+    ra.bound = opts["bound"]; ra.dt_gamma = opts["dt_gamma"]; ra.max_steps = opts["max_steps"]; ra.min_near = opts["min_near"]
+    ra.aabb = aabb.data_ptr(); ra.noises = noises.data_ptr() if noises is not None else None; ra.seed = opts["seed"]
+    ra.T_thresh = opts["T_thresh"]; ra.bg_color = bg_color.data_ptr() if bg_color is not None else None; ra.bg_scalar = 1.0
+    ra.max_depth = opts["max_depth"]
+    ra.smooth_noise = smooth_noise.data_ptr() if smooth_noise is not None else None
+    ra.noise_mode = opts.get("noise_mode", 0)
+    ra.all_counts = par["all_counts"].data_ptr() if par is not None else None
+    ra.n_ranks = par["world"] if par is not None else 1
+    ra.pad_view_mask = opts.get("pad_view_mask", (1 << ra.n_views) - 1)
+    return ra
 
 
 class _RenderTrain(Function):
+    """image, depth, weights_sum, loss_orient, loss_smooth = render(...) through mi3d_render_forward / mi3d_render_backward: ONE C call
+    per direction (march [+ray generation] -> fused field -> composite + epilogue).  With `par` (parallel.RayParallel) the batch is
+    this rank's share of every view of the step: per-view sample counts are all-gathered between the march and the field (device
+    side, no host sync), image fragments travel to the view's owner in one all-to-all, and the backward sends the gradient
+    fragments back the same way."""
+
+    @staticmethod
+    def forward(ctx, table, w1, b1, w2, b2, w3, b3, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color,
+                depth_scale, ws, hg, cfg, opts, raygen, par):
+        P = (w1, b1, w2, b2, w3, b3)
+        _check_params(table, P)
+        if rays_o is not None:
+            rays_o, rays_d = L.f32c(rays_o).view(-1, 3), L.f32c(rays_d).view(-1, 3)
+        L.require_cuda(rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color, depth_scale)
+        N = ws.N
+        if rays_o is not None and rays_o.shape[0] != N:
+            raise L.Mi3dError(f"workspace built for {ws.N} rays, got {rays_o.shape[0]}")
+        dev = table.device
+        lib = L.lib()
+        nv = opts.get("n_views", 1)
+        ws.generation += 1
+        pdict = None
+        if par is not None:
+            pdict = dict(world=par.world, all_counts=torch.empty(par.world, nv, dtype=torch.int32, device=dev))
+        ra = _render_args(ws, N, rays_o, rays_d, depth_scale, raygen, bitfield, aabb, noises, smooth_noise, bg_color, opts, pdict)
+        mlp, cf = _mlp_struct(P), _cfg_struct(cfg, light_d)
+        multi = nv > 1 or par is not None
+        losses = torch.zeros(2, nv if multi else 1, dtype=torch.float32, device=dev)
+        image = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        weights_sum = torch.empty(N, dtype=torch.float32, device=dev)
+
+        def call(phases):
+            L.check(lib.mi3d_render_forward(C.byref(ra), L.ptr(table), C.byref(hg), C.byref(mlp), C.byref(cf), C.byref(ws.c), C.c_int(phases),
+                                            L.ptr(image), L.ptr(depth), L.ptr(weights_sum), C.c_void_p(losses[0].data_ptr()),
+                                            C.c_void_p(losses[1].data_ptr()), L.stream()), "render_forward")
+        if par is None:
+            call(L.RENDER_PHASE_ALL)
+        else:
+            call(L.RENDER_PHASE_MARCH)
+            par.gather_counts(ws.view_counts[:nv], pdict["all_counts"])
+            call(L.RENDER_PHASE_SHADE)
+        ctx.set_materialize_grads(False)        # unused outputs arrive as None -> the backward skips evaluations that get no gradient
+        ctx.save_for_backward(table, w1, b1, w2, b2, w3, b3, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color, depth_scale)
+        ctx.ws, ctx.hg, ctx.cfg, ctx.opts, ctx.N, ctx.generation, ctx.raygen, ctx.par, ctx.pdict = ws, hg, cfg, opts, N, ws.generation, raygen, par, pdict
+        if par is not None:
+            # fragments [view][ray-in-fragment] -> the owner of each view; own view comes back complete
+            packed = torch.cat([image, depth[:, None], weights_sum[:, None]], dim=1)           # [N, 5]
+            full = par.fragments_to_owner(packed, nv)                                           # [N, 5] of this rank's view
+            lsum = par.reduce_losses(losses)                                                    # [2, nv] summed over ranks
+            image, depth, weights_sum = full[:, :3].contiguous(), full[:, 3].contiguous(), full[:, 4].contiguous()
+            return image, depth, weights_sum, lsum[0, par.rank], lsum[1, par.rank]
+        if multi:
+            return image, depth, weights_sum, losses[0], losses[1]
+        return image, depth, weights_sum, losses[0, 0], losses[1, 0]
+
+    @staticmethod
+    def backward(ctx, g_image, g_depth, g_ws, g_lo, g_ls):
+        (table, w1, b1, w2, b2, w3, b3, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color, depth_scale) = ctx.saved_tensors
+        ws, N, opts, par = ctx.ws, ctx.N, ctx.opts, ctx.par
+        if ws.generation != ctx.generation:
+            raise L.Mi3dError("render workspace was reused by a later forward before this backward ran")
+        P = (w1, b1, w2, b2, w3, b3)
+        lib = L.lib()
+        dev = table.device
+        nv = opts.get("n_views", 1)
+        g_image = L.f32c(g_image) if g_image is not None else torch.zeros(N, 3, dtype=torch.float32, device=dev)
+        g_depth, g_ws = _grad_or_none(g_depth), _grad_or_none(g_ws)
+        g_lo, g_ls = _grad_or_none(g_lo), _grad_or_none(g_ls)
+        if par is not None:
+            z = torch.zeros(N, dtype=torch.float32, device=dev)
+            packed = torch.cat([g_image, (g_depth if g_depth is not None else z)[:, None], (g_ws if g_ws is not None else z)[:, None]], dim=1)
+            frag = par.owner_to_fragments(packed, nv)                                            # [N, 5] in batch order
+            g_image, g_depth, g_ws = frag[:, :3].contiguous(), frag[:, 3].contiguous(), frag[:, 4].contiguous()
+            zero = torch.zeros((), dtype=torch.float32, device=dev)
+            gl = par.gather_loss_grads(torch.stack([g_lo if g_lo is not None else zero, g_ls if g_ls is not None else zero]))   # [world, 2]
+            had_lo, had_ls = g_lo is not None, g_ls is not None
+            g_lo, g_ls = (gl[:, 0].contiguous() if had_lo else None), (gl[:, 1].contiguous() if had_ls else None)
+        ra = _render_args(ws, N, rays_o, rays_d, depth_scale, ctx.raygen, bitfield, aabb, noises, smooth_noise, bg_color, opts, ctx.pdict)
+        g_table = torch.zeros_like(table)
+        g_P = [torch.zeros_like(w) for w in P]
+        mlp, cf, gm = _mlp_struct(P), _cfg_struct(ctx.cfg, light_d), _mlp_struct(g_P)
+        full = (g_lo is not None) or (g_ls is not None) or ctx.cfg["shading"] != "albedo"
+        _timed("render_bwd", dict(n_evals=ctx.cfg["n_evals"], N=N, full=full), lambda: L.check(lib.mi3d_render_backward(
+            C.byref(ra), L.ptr(table), C.byref(ctx.hg), C.byref(mlp), C.byref(cf), C.byref(ws.c), L.ptr(g_image), L.ptr(g_depth), L.ptr(g_ws),
+            L.ptr(g_lo), L.ptr(g_ls), L.ptr(g_table), C.byref(gm), L.ptr(bwd_scratch(table.device)), C.c_int(1), L.stream()), "render_backward"))
+        return (g_table, *g_P) + (None,) * 15
+
+
+def render_train(table, mlp_params, rays_o, rays_d, bitfield, aabb, ws, hg, cfg, opts, noises=None, light_d=None,
+                 smooth_noise=None, bg_color=None, depth_scale=None, raygen=None, par=None):
+    """Returns (image[N,3], depth[N], weights_sum[N], loss_orient, loss_smooth).  rays_o / rays_d explicit, or raygen (L.RayGen)
+    to generate them inside the march kernel.  opts['n_views'] > 1: multi-view batch (losses are [n_views]).  par: ray-parallel
+    multi-GPU step, outputs are this rank's own complete view."""
+    if PROFILE is not None and par is None and opts.get("n_views", 1) == 1 and rays_o is not None:
+        # bench.py's per-kernel roofline leg: the same kernels through the unfused entry points, CUDA events around the field calls
+        return _RenderTrainUnfused.apply(table, *mlp_params, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color,
+                                         depth_scale, ws, hg, cfg, opts)
+    return _RenderTrain.apply(table, *mlp_params, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color,
+                              depth_scale, ws, hg, cfg, opts, raygen, par)
+
+
+class _RenderTrainUnfused(Function):
+    """The same step through the separate B1 / B2 entry points (march, field, composite: three C calls + torch glue).  Kept as the
+    A/B arm of tests/test_field_gpu.py::test_fused_entry_points_match_unfused and for per-kernel CUDA-event timing (bench.py)."""
+
     @staticmethod
     def forward(ctx, table, w1, b1, w2, b2, w3, b3, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color,
                 depth_scale, ws, hg, cfg, opts):
@@ -202,7 +345,7 @@ class _RenderTrain(Function):
         io.xyzs = ws.xyzs.data_ptr(); io.dirs = ws.dirs.data_ptr(); io.counter = ws.counter.data_ptr()
         io.m_fixed = 0; io.align = 128; io.cap = ws.cap
         io.smooth_noise = smooth_noise.data_ptr() if smooth_noise is not None else None
-        io.seed = opts["seed"] + 1
+        io.seed = opts["seed"] + 1; io.noise_mode = opts.get("noise_mode", 0)
         io.enc_cache = ws.enc_cache.data_ptr(); io.enc_cache_tiles = ws.enc_tiles; io.enc_cache_valid = 0
         mlp, cf = _mlp_struct(P), _cfg_struct(cfg, light_d)
         losses = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -218,7 +361,7 @@ class _RenderTrain(Function):
         image = torch.empty(N, 3, dtype=torch.float32, device=dev)
         depth = torch.empty(N, dtype=torch.float32, device=dev)
         L.check(lib.mi3d_composite_rays_train_forward(
-            L.ptr(ws.sigmas), L.ptr(ws.rgbs), L.ptr(ws.deltas), L.ptr(ws.rays), C.c_uint32(ws.cap), C.c_uint32(N),
+            L.ptr(ws.sigmas), L.ptr(ws.rgbs), L.ptr(ws.deltas), L.ptr(ws.rays), C.c_uint32(ws.cap - 128), C.c_uint32(N),
             C.c_float(opts["T_thresh"]), L.ptr(ws.ws_raw), L.ptr(ws.depth_raw), L.ptr(ws.image_raw), C.byref(ep), L.ptr(image),
             L.ptr(depth), L.stream()), "composite_rays_train_forward")
         weights_sum = ws.ws_raw.clone()
@@ -246,7 +389,7 @@ class _RenderTrain(Function):
         ep.depth_scale = depth_scale.data_ptr() if depth_scale is not None else None
         L.check(lib.mi3d_composite_rays_train_backward(
             L.ptr(g_ws), L.ptr(g_image), L.ptr(g_depth), L.ptr(ws.sigmas), L.ptr(ws.rgbs), L.ptr(ws.deltas), L.ptr(ws.rays),
-            L.ptr(ws.ws_raw), L.ptr(ws.image_raw), C.c_uint32(ws.cap), C.c_uint32(N), C.c_float(opts["T_thresh"]), C.byref(ep),
+            L.ptr(ws.ws_raw), L.ptr(ws.image_raw), C.c_uint32(ws.cap - 128), C.c_uint32(N), C.c_float(opts["T_thresh"]), C.byref(ep),
             L.ptr(ws.g_sigmas), L.ptr(ws.g_rgbs), C.c_int(1), L.stream()), "composite_rays_train_backward")
         g_table = torch.zeros_like(table)
         g_P = [torch.zeros_like(w) for w in P]
@@ -254,7 +397,7 @@ class _RenderTrain(Function):
         io.xyzs = ws.xyzs.data_ptr(); io.dirs = ws.dirs.data_ptr(); io.counter = ws.counter.data_ptr()
         io.m_fixed = 0; io.align = 128; io.cap = ws.cap
         io.smooth_noise = smooth_noise.data_ptr() if smooth_noise is not None else None
-        io.seed = ctx.io_seed
+        io.seed = ctx.io_seed; io.noise_mode = opts.get("noise_mode", 0)
         io.enc_cache = ws.enc_cache.data_ptr(); io.enc_cache_tiles = ws.enc_tiles; io.enc_cache_valid = 1 if ctx.generation == ws.generation else 0
         mlp, cf, gm = _mlp_struct(P), _cfg_struct(ctx.cfg, light_d), _mlp_struct(g_P)
         g_lo, g_ls = _grad_or_none(g_lo), _grad_or_none(g_ls)
@@ -265,8 +408,3 @@ class _RenderTrain(Function):
         return (g_table, *g_P) + (None,) * 13
 
 
-def render_train(table, mlp_params, rays_o, rays_d, bitfield, aabb, ws, hg, cfg, opts, noises=None, light_d=None,
-                 smooth_noise=None, bg_color=None, depth_scale=None):
-    """Returns (image[N,3], depth[N], weights_sum[N], loss_orient, loss_smooth)."""
-    return _RenderTrain.apply(table, *mlp_params, rays_o, rays_d, bitfield, aabb, noises, light_d, smooth_noise, bg_color,
-                              depth_scale, ws, hg, cfg, opts)

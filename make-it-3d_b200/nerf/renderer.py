@@ -61,38 +61,90 @@ class NeRFRenderer(nn.Module):
         self.mean_count = 0
         self.local_step = 0
 
-    def _workspace(self, N, max_steps, device):
-        key = (N, max_steps, str(device))
+    def _workspace(self, N, max_steps, device, n_views=1):
+        key = (N, max_steps, str(device), n_views)
         ws = self._workspaces.get(key)
         if ws is None:
-            ws = field_ops.RenderWorkspace(N, max_steps, device, max_samples=getattr(self.opt, "max_samples", None))
+            ws = field_ops.RenderWorkspace(N, max_steps, device, max_samples=getattr(self.opt, "max_samples", None), n_views=n_views)
             self._workspaces = {key: ws}        # keep one (shapes are fixed during training)
         return ws
 
     def run_cuda(self, rays_o, rays_d, depth_scale=None, bg_color=None, dt_gamma=0, light_d=None, ambient_ratio=1.0,
                  shading='albedo', perturb=False, force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
-        """nerf/renderer.py:481-583.  Extra optional kwargs (additive): noises[N], smooth_noise[m,3] inject the random draws
-        of raymarching.py:226 / renderer.py:522 for reproducible parity tests."""
-        prefix = rays_o.shape[:-1]
-        rays_o = L.f32c(rays_o).view(-1, 3)
-        rays_d = L.f32c(rays_d).view(-1, 3)
-        L.require_cuda(rays_o, rays_d)
-        N = rays_o.shape[0]
-        device = rays_o.device
-
-        if light_d is None:                                            # renderer.py:496-499
-            light_d = safe_normalize(rays_o[0] + torch.randn(3, device=device, dtype=torch.float))
-        light_d = L.f32c(light_d)
+        """nerf/renderer.py:481-583.  Additive optional kwargs (none collides with a reference `opt` field):
+          noises[N], smooth_noise[m,3]  inject the random draws of raymarching.py:226 / renderer.py:522 (reproducible parity tests)
+          cam_poses [G,4,4], cam_intrinsics (fx,fy,cx,cy) or [G,4], cam_hw (H, W)
+                                        generate the rays of G views inside the march kernel (rays_o / rays_d may be None);
+                                        G > 1 = a multi-view batch: image [G,HW,3], per-view losses [G]
+          cam_table [G,16]              the same, as the ready device table of nerf/utils.py::camera_table (instead of cam_poses)
+          ray_parallel                  parallel.RayParallel: this rank renders every world-th pixel of each of `world` views and
+                                        returns the complete image of ITS OWN view (rank r owns cam_poses[r]); needs step_seed
+          step_seed                     int shared by all ranks of a step (march jitter, smoothness perturbation, light directions)"""
+        device = self.density_bitfield.device
+        cam_poses = kwargs.get('cam_poses')
+        cam_table = kwargs.get('cam_table')
+        if cam_table is not None:
+            L.require_cuda(cam_table)
+            cam_poses = cam_table
+        par = kwargs.get('ray_parallel')
+        if cam_poses is None:
+            prefix = rays_o.shape[:-1]
+            rays_o = L.f32c(rays_o).view(-1, 3)
+            rays_d = L.f32c(rays_d).view(-1, 3)
+            L.require_cuda(rays_o, rays_d)
+            N = rays_o.shape[0]
+            device = rays_o.device
+        elif not self.training:
+            raise L.Mi3dError("cam_poses (in-kernel ray generation) is a training-path option; pass rays for evaluation")
         results = {}
 
         if self.training:
             table, mlp_params, hg, cfg = self._field_handles()
             cfg = dict(cfg, n_evals=13 if self.opt.lambda_smooth > 0 else 7, shading=shading, ambient_ratio=float(ambient_ratio))
-            ws = self._workspace(N, max_steps, device)
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # CPU generator: no device sync
+            step_seed = kwargs.get('step_seed')
+            if par is not None and step_seed is None:
+                raise L.Mi3dError("ray_parallel needs step_seed (a value shared by all ranks, e.g. parallel.shared_seed(base, step))")
+            seed = int(step_seed) if step_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())   # CPU generator: no device sync
+            G, raygen, origins = 1, None, None
+            if cam_poses is not None:
+                from . import utils as U
+                Hc, Wc = kwargs['cam_hw']
+                if cam_table is not None:
+                    cams = L.f32c(cam_table).view(-1, 16)
+                else:
+                    cam_poses = torch.as_tensor(cam_poses, dtype=torch.float32)
+                    if cam_poses.dim() == 2:
+                        cam_poses = cam_poses[None]
+                    cams = U.camera_table(cam_poses, kwargs['cam_intrinsics'], device)
+                G = cams.shape[0]
+                if par is not None:
+                    if G != par.world or (Hc * Wc) % par.world:
+                        raise L.Mi3dError(f"ray_parallel: need one view per rank and H*W divisible by the world size (G={G}, world={par.world})")
+                    rpv = Hc * Wc // par.world
+                    raygen = U.raygen_struct(cams, Hc, Wc, rpv, par.world, par.rank)
+                else:
+                    rpv = Hc * Wc
+                    raygen = U.raygen_struct(cams, Hc, Wc, rpv, 1, 0)
+                self._cams = cams                                      # keep the device table alive until the backward ran
+                N = G * rpv
+                origins = cams[:, [3, 7, 11]]
+                rays_o = rays_d = None
+                prefix = (1, Hc * Wc) if (par is not None or G == 1) else (G, Hc * Wc)
+            elif par is not None:
+                raise L.Mi3dError("ray_parallel needs cam_poses (every rank generates its share of every view's rays)")
+            multi = G > 1 or par is not None
+            if light_d is None:                                        # renderer.py:496-499, one direction per view
+                gen = torch.Generator().manual_seed(seed % (2 ** 63)) if step_seed is not None else None
+                o = origins if origins is not None else rays_o[:1]
+                light_d = safe_normalize(o + torch.randn(o.shape, generator=gen).to(device))
+                if not multi:
+                    light_d = light_d[0]
+            light_d = L.f32c(light_d.to(device))
+            ws = self._workspace(N, max_steps, device, G)
             opts = dict(bound=float(self.bound), dt_gamma=float(dt_gamma), max_steps=int(max_steps), cascade=self.cascade,
                         grid_size=self.grid_size, min_near=0.2,          # wrapper default, NOT opt.min_near (raymarching.py:34)
-                        T_thresh=float(T_thresh), max_depth=float(self.opt.max_depth), seed=seed)
+                        T_thresh=float(T_thresh), max_depth=float(self.opt.max_depth), seed=seed, n_views=G,
+                        noise_mode=1 if (multi or step_seed is not None) else 0, pad_view_mask=(1 << par.rank) if par is not None else (1 << G) - 1)
             noises = kwargs.get('noises')
             if noises is None and not perturb:
                 noises = torch.zeros(N, dtype=torch.float32, device=device)
@@ -100,18 +152,27 @@ class NeRFRenderer(nn.Module):
                 bg_color = torch.full((3,), float(bg_color), device=device)
             if bg_color is not None:
                 bg_color = L.f32c(bg_color.to(device))
-            ds = L.f32c(depth_scale).view(-1) if depth_scale is not None else None
+                if multi and bg_color.dim() == 1:
+                    bg_color = bg_color.expand(G, 3).contiguous()
+            ds = L.f32c(depth_scale).view(-1) if (depth_scale is not None and raygen is None) else None
             self.local_step += 1
             image, depth, weights_sum, loss_orient, loss_smooth = field_ops.render_train(
                 table, mlp_params, rays_o, rays_d, self.density_bitfield, self.aabb_train, ws, hg, cfg, opts,
-                noises=noises, light_d=light_d, smooth_noise=kwargs.get('smooth_noise'), bg_color=bg_color, depth_scale=ds)
+                noises=noises, light_d=light_d, smooth_noise=kwargs.get('smooth_noise'), bg_color=bg_color, depth_scale=ds,
+                raygen=raygen, par=par)
             results['loss_orient'] = loss_orient
             if self.opt.lambda_smooth > 0:
                 results['loss_smooth'] = loss_smooth
             nears, fars = ws.nears, ws.fars
             image = image.view(*prefix, 3)
             depth = depth.view(*prefix, 1)
+            if par is not None:                                        # nears / fars cover this rank's ray share only
+                results['image'], results['depth'], results['weights_sum'] = image, depth, weights_sum.reshape(*prefix)
+                return results
         else:
+            if light_d is None:                                        # renderer.py:496-499
+                light_d = safe_normalize(rays_o[0] + torch.randn(3, device=device, dtype=torch.float))
+            light_d = L.f32c(light_d)
             nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_infer)
             dtype = torch.float32
             weights_sum = torch.zeros(N, dtype=dtype, device=device)
@@ -153,8 +214,11 @@ class NeRFRenderer(nn.Module):
         return results
 
     @torch.no_grad()
-    def update_extra_state(self, decay=0.95, S=128, jitter=None):
-        """nerf/renderer.py:587-637 as ONE C-ABI call (positions, field, EMA-max, mean, packbits); no .item()."""
+    def update_extra_state(self, decay=0.95, S=128, jitter=None, seed=None):
+        """nerf/renderer.py:587-637 as ONE C-ABI call (positions, field, EMA-max, mean, packbits); no .item().
+        `seed` (additive kwarg) keys the in-kernel cell jitter.  Multi-GPU callers MUST pass the same value on every rank
+        (parallel.shared_seed(base, iteration)): the view-/ray-parallel step relies on bit-identical bitfields without a
+        broadcast.  None draws from this process's CPU generator (single-process behaviour of the reference)."""
         table, mlp_params, hg, cfg = self._field_handles()
         dev = table.device
         lib = L.lib()
@@ -164,7 +228,8 @@ class NeRFRenderer(nn.Module):
             self._mean_density_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         cf = field_ops._cfg_struct(dict(cfg, n_evals=1, shading='albedo', ambient_ratio=1.0), None)
         mlp = field_ops._mlp_struct(mlp_params)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         if jitter is not None:
             jitter = L.f32c(jitter)
         L.check(lib.mi3d_density_grid_update(

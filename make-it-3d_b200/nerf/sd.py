@@ -6,8 +6,8 @@ guidance_scale=10) -> (loss, imgs)` performs the SDS backward itself into pred_r
 engine of csrc/sd_engine.cu (tcgen05 tile kernel + fused memory-bound kernels); there is no diffusers / cuDNN / cuBLAS
 call and no CPU fallback.
 
-Weights: parameters carry diffusers' state_dict names (`unet.*`, `vae.*`) so real SD-2.0-base checkpoints load with
-`load_state_dict`; offline (no network, no weights on disk) they are seeded random tensors with PyTorch's default
+Weights: parameters are enumerated by diffusers' state_dict names; real SD-2.0-base checkpoints load through
+`load_diffusers_state_dict(unet_state, vae_state)` (which also pushes them into the engine); offline (no network, no weights on disk) they are seeded random tensors with PyTorch's default
 initialisers -- which is what the benchmark and the parity tests use (`data: synthetic`).
 What is NOT built ("next"): the text encoder, VAE decoder and the CLIP "denoise" side branch
 (nerf/sd.py:153-159).  That branch yields no gradient to any optimised parameter; here it returns (0, None) without
@@ -15,6 +15,7 @@ running, which leaves the optimisation trajectory identical.
 """
 import contextlib
 import ctypes as C
+import hashlib
 import math
 import os
 
@@ -74,7 +75,7 @@ def alphas_cumprod(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012)
 class SDEngine:
     """Owns the device workspace and the planned launch lists (mi3d_sd_create)."""
 
-    def __init__(self, unet_cfg, vae_cfg, device):
+    def __init__(self, unet_cfg, vae_cfg, device, graph_replay=True):
         lib = L.lib()
         lib.mi3d_sd_workspace_bytes.restype = C.c_size_t
         lib.mi3d_sd_create.restype = C.c_void_p
@@ -98,10 +99,15 @@ class SDEngine:
             r = lib.mi3d_sd_param_shape(self.h, C.c_int(i), shp)
             self.shapes.append(tuple(shp[k] for k in range(r)))
         self.nbytes = nbytes
-        # Opt-in (MI3D_SD_STREAM=1, together with MI3D_SD_GRAPH=1): run the launch lists on the engine's own stream.  torch's default
-        # stream is the legacy stream, which CUDA cannot capture; on a side stream the lists replay as graphs (measured
-        # -1.35 ms per guidance step, tools/prof_sd.py).  Off by default until the parity suite has run under replay.
-        self.stream = torch.cuda.Stream(device) if os.environ.get("MI3D_SD_STREAM") == "1" else None
+        # The launch lists run on the engine's own stream (event-ordered against the caller's, see on_stream) and replay as CUDA
+        # graphs from their third call on: torch's default stream is the legacy stream, which CUDA cannot capture.
+        # graph_replay=False keeps plain launches on the caller's stream (used by the parity tests as the A/B arm).
+        self.stream = torch.cuda.Stream(device) if graph_replay else None
+        L.check(lib.mi3d_sd_set_graph_replay(self.h, C.c_int(1 if graph_replay else 0)), "sd_set_graph_replay")
+
+    def graph_replays(self):
+        """number of launch lists currently instantiated as CUDA graphs (0..3)"""
+        return int(L.lib().mi3d_sd_graph_replays(self.h))
 
     @contextlib.contextmanager
     def on_stream(self):
@@ -190,7 +196,7 @@ class _EncodeImgs(torch.autograd.Function):
 
 class StableDiffusion(nn.Module):
     def __init__(self, device, sd_version='2.0', hf_key=None, step_range=[0.2, 0.6], unet_cfg=None, vae_cfg=None, seed=0,
-                 unet_state=None, vae_state=None):
+                 unet_state=None, vae_state=None, graph_replay=True):
         super().__init__()
         self.device = torch.device(device)
         self.sd_version = sd_version
@@ -198,7 +204,7 @@ class StableDiffusion(nn.Module):
             raise ValueError(f'Stable-diffusion version {sd_version} not built (reference default is 2.0, nerf/sd.py:33-34)')
         self.unet_cfg = unet_cfg or sd20_unet_cfg()
         self.vae_cfg = vae_cfg or sd_vae_cfg()
-        self.engine = SDEngine(self.unet_cfg, self.vae_cfg, self.device)
+        self.engine = SDEngine(self.unet_cfg, self.vae_cfg, self.device, graph_replay=graph_replay)
         gen = torch.Generator().manual_seed(seed)
         # parameter containers with diffusers names: unet.<name>, vae.<name>
         self.unet = nn.ParameterDict()
@@ -242,7 +248,8 @@ class StableDiffusion(nn.Module):
         out = []
         for s in (negative_prompt, prompt):
             s = s[0] if isinstance(s, (list, tuple)) else s
-            g = torch.Generator().manual_seed(abs(hash(("mi3d", s))) % (2 ** 31))
+            # stable digest (python's hash() is salted per process: every rank would get different text conditioning)
+            g = torch.Generator().manual_seed(int.from_bytes(hashlib.sha256(("mi3d:" + s).encode()).digest()[:4], "little"))
             out.append(torch.randn(1, 77, D, generator=g))
         return torch.cat(out).to(self.device)
 

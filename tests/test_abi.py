@@ -87,8 +87,8 @@ def test_committed_bench_line_has_every_contract_key():
     assert line["gpu_launches"] > 0 and not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-def test_engine_stream_context_is_a_no_op_by_default():
-    """MI3D_SD_STREAM unset: SDEngine.on_stream() must not touch streams (the engine then launches on the caller's stream)"""
+def test_engine_stream_context_is_a_no_op_without_graph_replay():
+    """graph_replay=False (engine.stream is None): SDEngine.on_stream() must not touch streams (launches go to the caller's stream)"""
     import importlib
     sd = importlib.import_module("make-it-3d_b200.nerf.sd")
 
@@ -98,3 +98,32 @@ def test_engine_stream_context_is_a_no_op_by_default():
     with sd.SDEngine.on_stream(_E()):
         ran.append(1)
     assert ran == [1]
+
+
+def test_backend_mi3d_covers_reference_call_sites():
+    """Every `get_backend().<name>(...)` call in the REFERENCE's raymarching/raymarching.py must resolve on backend_mi3d._backend
+    with the same positional arity (build container only: /root/reference is absent on the GPU box)."""
+    import ast
+    import importlib
+    import inspect
+    import os
+
+    import pytest
+    path = "/root/reference/raymarching/raymarching.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    be = importlib.import_module("make-it-3d_b200.backend_mi3d")._backend
+    calls = {}
+    for node in ast.walk(ast.parse(open(path).read())):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Call) \
+                and getattr(node.func.value.func, "id", "") == "get_backend":
+            calls.setdefault(node.func.attr, set()).add(len(node.args))
+    assert {"near_far_from_aabb", "march_rays_train", "composite_rays_train_forward", "composite_rays_train_backward", "packbits",
+            "morton3D", "morton3D_invert", "march_rays", "composite_rays"} <= set(calls)
+    for name, arities in calls.items():
+        assert hasattr(be, name), name
+        fn = getattr(be, name)
+        params = list(inspect.signature(fn).parameters.values())
+        if any(p.kind == p.VAR_POSITIONAL for p in params):
+            continue                                   # the loudly-failing stubs of unreachable entry points
+        assert arities == {len(params)}, (name, arities, len(params))

@@ -108,12 +108,14 @@ def test_density_matches_oracle_and_k1_backward():
     assert max_abs(net.sigma_net.net[1].weight.grad.cpu(), q) / float(q.abs().max()) < 1e-3
 
 
+@pytest.mark.parametrize("impl", ["tcgen05", "ffma"])
 @pytest.mark.parametrize("case", ["albedo", "lambertian", "textureless"])
-def test_fused_render_step_matches_reference_golden(case):
+def test_fused_render_step_matches_reference_golden(case, impl):
     """The drop-in call Trainer.train_step makes (model.render(...), nerf/utils.py:496) on the fused CUDA path vs the
-    golden vectors recorded from the reference's Python: image / depth / weights_sum / losses and parameter gradients."""
+    golden vectors recorded from the reference's Python: image / depth / weights_sum / losses and parameter gradients.
+    Both kernel families (mi3d_field_cfg.impl: tcgen05 split-precision tiles, fp32 FFMA tiles) are held to the same bounds."""
     g = load_golden(f"render_{case}.npz")
-    net = _net_from_golden(g)
+    net = _net_from_golden(g, field_impl=impl)
     net.train()
     net.density_bitfield = _cu(sphere_bitfield(float(g["radius"])))
     out = net.render(_cu(g["rays_o"])[None], _cu(g["rays_d"])[None], depth_scale=_cu(g["depth_scale"])[None], bg_color=_cu(g["bg_color"]),
@@ -214,3 +216,44 @@ def test_update_extra_state_matches_oracle():
     mean = float(got.astype(np.float64).mean())
     assert abs(float(net.mean_density) / mean - 1) < 1e-5
     np.testing.assert_array_equal(net.density_bitfield.cpu().numpy(), orm.packbits(got, min(mean, 10.0)))
+
+
+def test_march_overflow_exposes_only_written_rows():
+    """opt.max_samples caps the per-sample buffers below N*max_steps: rays that do not fit write nothing
+    (raymarching.cu:416) and counter[0] must then be the emitted prefix, so that the field kernels never touch unwritten rows
+    (nothing is zero-filled here, unlike raymarching.py:217-219).  Dropped rays composite to the background."""
+    from helpers import camera_rays
+    g = load_golden("render_albedo.npz")
+    cap = 20000
+    net = _net_from_golden(g, max_samples=cap)
+    net.train()
+    net.density_bitfield = _cu(sphere_bitfield(0.3))
+    HW = 64
+    ro, rd, sc = camera_rays(HW)
+    noises = np.random.default_rng(5).random(HW * HW, dtype=np.float32)
+    bg = np.array([0.2, 0.5, 0.7], np.float32)
+    kw = dict(depth_scale=_cu(sc)[None], bg_color=_cu(bg), perturb=True, light_d=_cu(g["light_d"]), shading="lambertian", ambient_ratio=0.1,
+              force_all_rays=True, max_steps=512, noises=_cu(noises))
+    out = net.render(_cu(ro)[None], _cu(rd)[None], **kw)
+    ws = list(net._workspaces.values())[0]
+    ws.xyzs.fill_(float("nan")); ws.tape.fill_(float("nan"))          # poison: a second render must not read stale / unwritten rows
+    out = net.render(_cu(ro)[None], _cu(rd)[None], **kw)
+    rays = ws.rays.cpu().numpy()
+    total_uncapped = int(rays[:, 2].sum())
+    assert total_uncapped > cap, "test must overflow"
+    fits = (rays[:, 1] + rays[:, 2]) <= cap
+    emitted = int(rays[fits, 2].sum())
+    assert int(ws.counter[0]) == emitted and emitted <= cap
+    assert np.all(np.diff(fits.astype(np.int8)) <= 0)                  # dropped rays are a suffix (ray-ordered compaction)
+    assert torch.isfinite(out["image"]).all() and torch.isfinite(out["loss_orient"]) and torch.isfinite(out["loss_smooth"])
+    dropped = torch.from_numpy(~fits & (rays[:, 2] > 0)).cuda()
+    assert torch.equal(out["image"][0][dropped], _cu(bg).expand(int(dropped.sum()), 3))
+    (out["image"].sum() + out["loss_orient"] + out["loss_smooth"]).backward()
+    assert torch.isfinite(net.encoder.params.grad).all() and all(torch.isfinite(p.grad).all() for p in net.sigma_net.parameters())
+    # same result as a render given only the rays that fit (the cap changes nothing for them)
+    n_fit = int(fits.sum())
+    net2 = _net_from_golden(g)
+    net2.train(); net2.density_bitfield = net.density_bitfield
+    kw2 = dict(kw, depth_scale=_cu(sc[:n_fit])[None], noises=_cu(noises[:n_fit]))
+    ref = net2.render(_cu(ro[:n_fit])[None], _cu(rd[:n_fit])[None], **kw2)
+    assert torch.equal(ref["image"][0], out["image"][0][:n_fit])

@@ -126,3 +126,58 @@ def test_render_restatement_matches_reference_python(case):
     gt = field.encoder.params.grad.numpy()
     assert rel_err(gt[g["g_table_idx"]], g["g_table_val"], floor=1e-4) < 1e-3
     assert abs(np.sqrt((gt.astype(np.float64) ** 2).sum()) / float(g["g_table_l2"]) - 1) < 1e-5
+
+
+def test_sd_oracle_two_independent_restatements_agree():
+    """Pin for oracle/sd_ref.py (diffusers is absent offline): the module-tree restatement and the functional,
+    state_dict-driven restatement (oracle/sd_ref2.py, written separately on torch.nn.functional building blocks) compute the same
+    U-Net and VAE-encoder outputs, and the SD-2.0-base / SD VAE topologies reproduce the published parameter counts."""
+    from oracle import sd_ref, sd_ref2
+    torch.manual_seed(0)
+    ucfg, vcfg = sd_ref.tiny_unet_config(), sd_ref.tiny_vae_config()
+    unet, vae = sd_ref.UNet2DConditionModel(ucfg).eval(), sd_ref.AutoencoderKLEncoder(vcfg).eval()
+    with torch.no_grad():
+        for m in list(unet.modules()) + list(vae.modules()):
+            if isinstance(m, (torch.nn.GroupNorm, torch.nn.LayerNorm)):
+                m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.3, 0.3)
+    g = torch.Generator().manual_seed(1)
+    x, ctx = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 77, ucfg["cross_dim"], generator=g)
+    img = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+    with torch.no_grad():
+        a = unet(x, torch.tensor([437]), ctx)
+        b = sd_ref2.unet_forward(unet.state_dict(), x, 437, ctx)
+        ma, la = vae(img)
+        mb, lb = sd_ref2.vae_encode_moments(vae.state_dict(), img)
+    assert float((a - b).abs().max()) < 2e-5 * float(a.abs().max())
+    assert float((ma - mb).abs().max()) < 2e-5 * float(ma.abs().max()) and float((la - lb).abs().max()) < 2e-5 * max(1.0, float(la.abs().max()))
+    # published sizes: stabilityai/stable-diffusion-2-base unet 865 910 724 parameters; SD VAE encoder + quant_conv 34 163 664
+    with torch.device("meta"):
+        big_u = sd_ref.UNet2DConditionModel(sd_ref.sd20_unet_config())
+        big_v = sd_ref.AutoencoderKLEncoder(sd_ref.sd_vae_config())
+    assert sum(p.numel() for p in big_u.parameters()) == 865910724
+    assert sum(p.numel() for p in big_v.parameters()) == 34163592 + 72          # encoder 34 163 592 + quant_conv 8*8+8
+    # the scheduler constants: SD scheduler_config.json (scaled_linear 0.00085 .. 0.012, 1000 steps), known end points
+    ac = sd_ref.alphas_cumprod()
+    assert abs(float(ac[0]) - 0.99915) < 1e-6 and abs(float(ac[999]) - 0.0046602) < 1e-6
+
+
+def test_sd_oracle_vs_diffusers_fixtures():
+    """When tools/dump_diffusers_fixtures.py has been run on a machine WITH diffusers (none here: no network, package absent),
+    tests/golden/diffusers_tiny.npz pins oracle/sd_ref.py against the real package.  Skipped until such a fixture exists."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "diffusers_tiny.npz")
+    if not os.path.exists(path):
+        pytest.skip("no diffusers fixture committed (diffusers unavailable offline; DESIGN.md 'Oracle status')")
+    from oracle import sd_ref
+    z = dict(np.load(path))
+    unet = sd_ref.UNet2DConditionModel(sd_ref.tiny_unet_config()).eval()
+    unet.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("unet.")})
+    vae = sd_ref.AutoencoderKLEncoder(sd_ref.tiny_vae_config()).eval()
+    vae.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("vae.")})
+    with torch.no_grad():
+        out = unet(torch.from_numpy(z["in.x"]), torch.tensor([int(z["in.t"])]), torch.from_numpy(z["in.ctx"]))
+        mean, logvar = vae(torch.from_numpy(z["in.img"]))
+    np.testing.assert_allclose(out.numpy(), z["out.unet"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(mean.numpy(), z["out.mean"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(logvar.numpy(), z["out.logvar"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(sd_ref.alphas_cumprod().numpy(), z["out.alphas_cumprod"], rtol=1e-6)

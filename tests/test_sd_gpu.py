@@ -108,3 +108,35 @@ def test_train_step_drop_in_semantics(tiny):
     rgb2 = rgb.detach().clone().requires_grad_()
     loss, imgs = g.train_step(ctx, rgb2, islarge=False, t=300)
     assert loss == 0 and imgs is None and rgb2.grad is None
+
+
+def test_graph_replay_is_bit_identical_to_plain_launches(tiny):
+    """The three static launch lists replay as CUDA graphs from their third call on (engine-owned stream; default since round 2).
+    Replay must reproduce the plain-launch results (same kernels, same order: differences can only come from the order of
+    the fp64 GroupNorm-statistics / split-K atomics, bounded here at 1e-5 of the tensor's scale), for the U-Net list and both VAE lists."""
+    sdm, g, unet, vae = tiny
+    gen = torch.Generator().manual_seed(7)
+    lat = (torch.randn(1, 4, 32, 32, generator=gen) * 0.8).cuda()
+    noise = torch.randn(1, 4, 32, 32, generator=gen).cuda()
+    ctx = torch.randn(2, 77, 128, generator=gen).cuda()
+    rgb = torch.rand(1, 3, 64, 64, generator=gen).cuda()
+    eps = torch.randn(1, 4, 32, 32, generator=gen).cuda()
+    glat = torch.randn(1, 4, 32, 32, generator=gen).cuda()
+    tt = torch.tensor([512], dtype=torch.long, device="cuda")
+    plain = sdm.StableDiffusion("cuda", unet_cfg=g.unet_cfg, vae_cfg=g.vae_cfg, unet_state=unet.state_dict(), vae_state=vae.state_dict(),
+                                graph_replay=False)
+    assert plain.engine.stream is None and g.engine.stream is not None
+
+    def one(m):
+        npred, grad = m.unet_sds(lat, noise, tt, ctx, 10.0)
+        r = rgb.clone().requires_grad_()
+        z = m.encode_imgs(r, eps)
+        z.backward(glat)
+        torch.cuda.synchronize()
+        return npred.clone(), grad.clone(), z.detach().clone(), r.grad.clone()
+    want = one(plain)
+    for call in range(4):
+        got = one(g)
+        for a, b in zip(got, want):
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()), call
+    assert g.engine.graph_replays() == 3 and plain.engine.graph_replays() == 0

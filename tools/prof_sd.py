@@ -52,7 +52,6 @@ def gemm_dump(g, rgb, ctx):
     import ctypes as C
     L = importlib.import_module("make-it-3d_b200._lib")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    os.environ["MI3D_SD_PROFILE_DUMP"] = os.path.join(ROOT, "gpurun_out", "sd_gemms.txt")
     L.check(L.lib().mi3d_sd_profile(g.engine.h, C.c_int(1), None, None), "sd_profile")
     rgb.grad = None
     lat = g.encode_imgs(rgb)
@@ -60,7 +59,7 @@ def gemm_dump(g, rgb, ctx):
     lat.backward(gradient=grad)
     torch.cuda.synchronize()
     ms, n = C.c_float(0), C.c_int(0)
-    L.check(L.lib().mi3d_sd_profile(g.engine.h, C.c_int(0), C.byref(ms), C.byref(n)), "sd_profile")
+    L.check(L.lib().mi3d_sd_profile_dump(g.engine.h, C.c_int(0), C.byref(ms), C.byref(n), os.path.join(ROOT, "gpurun_out", "sd_gemms.txt").encode()), "sd_profile_dump")
     print(f"tile kernel: {n.value} launches, {ms.value:.3f} ms")
 
 
