@@ -305,6 +305,28 @@ int mi3d_density_grid_update(float* density_grid, uint8_t* density_bitfield, uin
                              float* mean_density_out, void* workspace, mi3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Parameter update that follows the hot path: nn.utils.clip_grad_norm(max_norm) (nerf/utils.py:984) +
+ * Adan.step() with its own global-norm clip (optimizer.py:102-198) + _single_tensor_adan (optimizer.py:201-256) in one
+ * elementwise kernel over a flat (shard of a) parameter vector.  The global gradient norm stays on the device.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    double lr;              /* group['lr'] (python floats of the reference are doubles; the host folds them in double) */
+    double beta1, beta2, beta3, eps, weight_decay;     /* (0.98, 0.92, 0.99), 1e-8, 2e-5 (main.py:132) */
+    float max_grad_norm;    /* Adan's global clip, 5.0; 0 = off */
+    float clip_grad_norm;   /* Trainer's clip_grad_norm max_norm, 10; 0 = off */
+    int no_prox;
+    int step;               /* group['step'] AFTER the increment: 1 on the first call */
+    int reset_prev;         /* != 0: treat neg_pre_grad as missing (optimizer.py:160) */
+} mi3d_adan_cfg;
+/* out (+)= sum(g[i]^2), deterministic (fixed-order partials, fp64 fold).  g 16-byte aligned.  workspace: mi3d_sumsq_workspace_bytes(). */
+size_t mi3d_sumsq_workspace_bytes(void);
+int mi3d_sumsq(const float* g, uint64_t n, float* out, int accumulate, void* workspace, mi3d_stream_t stream);
+/* total_sumsq: DEVICE scalar = squared L2 norm of ALL gradients of the model before any clipping (every rank passes the global
+ * value).  grad is rescaled in place like the reference does (p.grad ends up clipped); all state tensors are updated in place. */
+int mi3d_adan_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, float* exp_avg_diff, float* neg_pre_grad, uint64_t n,
+                   const float* total_sumsq, const mi3d_adan_cfg* cfg, mi3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * B3: Stable-Diffusion guidance  (replaces the diffusers/cuDNN/cuBLAS calls behind nerf/sd.py:117-174, :212-220)
  * ------------------------------------------------------------------------------------------------------ */
 

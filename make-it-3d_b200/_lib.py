@@ -55,6 +55,12 @@ class ViewSegs(C.Structure):
     _fields_ = [("n_views", C.c_uint32), ("bounds", C.c_uint32 * (2 * MAX_VIEWS + 1)), ("mpad", C.c_uint32 * MAX_VIEWS)]
 
 
+class AdanCfg(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("beta3", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("max_grad_norm", C.c_float), ("clip_grad_norm", C.c_float), ("no_prox", C.c_int),
+                ("step", C.c_int), ("reset_prev", C.c_int)]
+
+
 class RenderArgs(C.Structure):
     _fields_ = [("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("depth_scale", C.c_void_p), ("raygen", C.POINTER(RayGen)), ("N", C.c_uint32),
                 ("n_views", C.c_uint32), ("density_bitfield", C.c_void_p), ("C", C.c_uint32), ("H", C.c_uint32), ("bound", C.c_float),
@@ -86,6 +92,7 @@ SYMBOLS = [
     "mi3d_field_grid_ctas", "mi3d_field_forward", "mi3d_field_backward", "mi3d_field_backward_workspace_bytes", "mi3d_field_enc_cache_bytes",
     "mi3d_render_workspace_bytes", "mi3d_render_workspace_carve", "mi3d_render_forward", "mi3d_render_backward",
     "mi3d_density_grid_workspace_bytes", "mi3d_density_grid_update", "mi3d_version",
+    "mi3d_sumsq_workspace_bytes", "mi3d_sumsq", "mi3d_adan_step",
     "mi3d_gemm_f16", "mi3d_gemm_f16_splitk", "mi3d_flash_attn_f16", "mi3d_conv3x3_f16", "mi3d_tf32_tile_test", "mi3d_gemm_f16_bt",
     "mi3d_sd_workspace_bytes", "mi3d_sd_create", "mi3d_sd_destroy", "mi3d_sd_num_params", "mi3d_sd_param_name", "mi3d_sd_param_numel",
     "mi3d_sd_param_shape", "mi3d_sd_load_param", "mi3d_sd_encode", "mi3d_sd_encode_backward", "mi3d_sd_unet_sds", "mi3d_sd_debug_tensor", "mi3d_sd_profile",
@@ -115,6 +122,7 @@ def lib():
         _lib.mi3d_field_backward_workspace_bytes.restype = C.c_size_t
         _lib.mi3d_field_enc_cache_bytes.restype = C.c_size_t
         _lib.mi3d_render_workspace_bytes.restype = C.c_size_t
+        _lib.mi3d_sumsq_workspace_bytes.restype = C.c_size_t
         for name in ("mi3d_sd_workspace_bytes", "mi3d_sd_weight_bytes"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_size_t

@@ -279,31 +279,53 @@ k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d
 // Training composite (+ optional fused epilogue of NeRFRenderer.run_cuda: background mix, far-depth fill,
 // depth_scale).  image_raw/ws are what the backward needs; image/depth are what the caller sees.
 // ---------------------------------------------------------------------------------------------
+// One WARP per ray: lanes take consecutive samples of the ray (coalesced 4 / 8 / 12-byte-stride loads instead of one thread striding
+// through its ray), transmittance and the depth parameter come from warp scans, the early-out (raymarching.cu:565: stop after the
+// sample that drives T below T_thresh) becomes a per-sample mask T_before >= T_thresh (T is monotone) plus a warp-uniform break.
+// Same arithmetic per sample as the reference; only the association order of the running product / sums differs (~1e-7).
 __global__ void __launch_bounds__(kRayThreads)
 k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
                       const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
                       float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
                       const float* __restrict__ bg_color, float bg_scalar, int fuse_epilogue, float max_depth,
                       const float* __restrict__ depth_scale, float* __restrict__ image_out, float* __restrict__ depth_out, uint32_t rays_per_view) {
-    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    const uint32_t n = (threadIdx.x + blockIdx.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
     if (n >= N) return;
     const uint32_t index = (uint32_t)rays[3 * (size_t)n], off = (uint32_t)rays[3 * (size_t)n + 1], cnt = (uint32_t)rays[3 * (size_t)n + 2];
     if (bg_color && rays_per_view) bg_color += 3 * (size_t)(index / rays_per_view);    // one background colour per view of the batch
-    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+    float T = 1.0f, t = 0.f, r = 0, g = 0, b = 0, ws = 0, d = 0;                      // T, t: carried across 32-sample chunks (warp-uniform)
     if (cnt != 0 && off + cnt <= M) {
         const float* sg = sigmas + off; const float* cl = rgbs + 3 * (size_t)off; const float* dl = deltas + 2 * (size_t)off;
-        for (uint32_t s = 0; s < cnt; s++) {
-            const float2 de = *reinterpret_cast<const float2*>(dl + 2 * s);
-            const float alpha = 1.0f - __expf(-sg[s] * de.x);
-            const float w = alpha * T;
-            r += w * cl[3 * s]; g += w * cl[3 * s + 1]; b += w * cl[3 * s + 2];
-            t += de.y;
-            d += w * t;
-            ws += w;
-            T *= 1.0f - alpha;
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            const uint32_t s = base + lane;
+            const bool valid = s < cnt;
+            float alpha = 0.f, dy = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (valid) {
+                const float2 de = *reinterpret_cast<const float2*>(dl + 2 * s);
+                alpha = 1.0f - __expf(-sg[s] * de.x); dy = de.y;
+                c0 = cl[3 * s]; c1 = cl[3 * s + 1]; c2 = cl[3 * s + 2];
+            }
+            float om = 1.0f - alpha, tt = dy;                          // inclusive scans: product of (1 - alpha), sum of deltas[:,1]
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float pm = __shfl_up_sync(0xffffffffu, om, o), pt = __shfl_up_sync(0xffffffffu, tt, o);
+                if ((int)lane >= o) { om *= pm; tt += pt; }
+            }
+            float T_before = __shfl_up_sync(0xffffffffu, om, 1);
+            T_before = T * (lane == 0 ? 1.0f : T_before);
+            const float w = (valid && T_before >= T_thresh) ? alpha * T_before : 0.f;
+            r += w * c0; g += w * c1; b += w * c2; ws += w; d += w * (t + tt);
+            T *= __shfl_sync(0xffffffffu, om, 31);
+            t += __shfl_sync(0xffffffffu, tt, 31);
             if (T < T_thresh) break;
         }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            r += __shfl_xor_sync(0xffffffffu, r, o); g += __shfl_xor_sync(0xffffffffu, g, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+            ws += __shfl_xor_sync(0xffffffffu, ws, o); d += __shfl_xor_sync(0xffffffffu, d, o);
+        }
     }
+    if (lane != 0) return;
     weights_sum[index] = ws; depth[index] = d;
     image[3 * (size_t)index] = r; image[3 * (size_t)index + 1] = g; image[3 * (size_t)index + 2] = b;
     if (fuse_epilogue) {
@@ -499,7 +521,7 @@ int mi3d_composite_rays_train_forward(const float* sigmas, const float* rgbs, co
     if (N == 0) return MI3D_OK;
     const int fuse = ep != nullptr;
     if (fuse && (!image_out || !depth_out)) return MI3D_ERR_ARG;
-    k_composite_train_fwd<<<mi3d_ceil_div(N, kRayThreads), kRayThreads, 0, (cudaStream_t)stream>>>(
+    k_composite_train_fwd<<<mi3d_ceil_div(N, kRayThreads / 32), kRayThreads, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image,
         fuse ? ep->bg_color : nullptr, fuse ? ep->bg_scalar : 0.f, fuse, fuse ? ep->max_depth : 0.f,
         fuse ? ep->depth_scale : nullptr, image_out, depth_out, fuse ? ep->rays_per_view : 0u);

@@ -74,10 +74,8 @@ __device__ __forceinline__ void gn_group_consts(const double* __restrict__ stats
 }
 
 __global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, int pix_per_cta, double* __restrict__ stats /*[N][G][2]*/) {
-    extern __shared__ float sm[];                 // [C][2]
+    extern __shared__ float sm[];                 // [PL][C][2]: one slot per thread, folded in a FIXED order (run-to-run deterministic)
     const int n = blockIdx.y, cpg = C / G, VPP = C / 8, PL = blockDim.x / VPP;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
     const int pl = threadIdx.x / VPP, cv = threadIdx.x % VPP;
     const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
     float s[8], ss[8];
@@ -85,19 +83,34 @@ __global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, i
     for (int k = 0; k < 8; k++) { s[k] = 0.f; ss[k] = 0.f; }
     if (pl < PL) {
         const __half* base = x + ((size_t)n * HW) * C + (size_t)cv * 8;
-        for (int p = p0 + pl; p < p1; p += PL) {
+        // 4 independent 16-byte loads in flight per thread: with 2 CTAs x 8 warps per SM a single load per iteration left the
+        // kernel latency-bound at ~1.5 TB/s (Little's law); the pixel order of the sums is unchanged (still deterministic)
+        int p = p0 + pl;
+        for (; p + 3 * PL < p1; p += 4 * PL) {
+            uint4 raw[4];
+            #pragma unroll
+            for (int u = 0; u < 4; u++) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(p + u * PL) * C));
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const __half* h = reinterpret_cast<const __half*>(&raw[u]);
+                #pragma unroll
+                for (int k = 0; k < 8; k++) { const float v = __half2float(h[k]); s[k] += v; ss[k] = fmaf(v, v, ss[k]); }
+            }
+        }
+        for (; p < p1; p += PL) {
             const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (size_t)p * C));
             const __half* h = reinterpret_cast<const __half*>(&raw);
             #pragma unroll
             for (int k = 0; k < 8; k++) { const float v = __half2float(h[k]); s[k] += v; ss[k] = fmaf(v, v, ss[k]); }
         }
         #pragma unroll
-        for (int k = 0; k < 8; k++) { atomicAdd(&sm[2 * (cv * 8 + k)], s[k]); atomicAdd(&sm[2 * (cv * 8 + k) + 1], ss[k]); }
+        for (int k = 0; k < 8; k++) { sm[2 * (pl * C + cv * 8 + k)] = s[k]; sm[2 * (pl * C + cv * 8 + k) + 1] = ss[k]; }
     }
     __syncthreads();
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double a = 0, b = 0;
-        for (int c = g * cpg; c < (g + 1) * cpg; c++) { a += sm[2 * c]; b += sm[2 * c + 1]; }
+        for (int c = g * cpg; c < (g + 1) * cpg; c++)
+            for (int q = 0; q < PL; q++) { a += sm[2 * (q * C + c)]; b += sm[2 * (q * C + c) + 1]; }
         atomicAdd(&stats[((size_t)n * G + g) * 2], a); atomicAdd(&stats[((size_t)n * G + g) * 2 + 1], b);
     }
 }
@@ -119,8 +132,7 @@ __global__ void k_gn_apply(const __half* __restrict__ x, __half* __restrict__ y,
     }
     const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
     const size_t base = ((size_t)n * HW) * C + (size_t)cv * 8;
-    for (int p = p0 + pl; p < p1; p += PL) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
+    auto one = [&](const uint4& raw, int p) {
         const __half* h = reinterpret_cast<const __half*>(&raw);
         __align__(16) __half o[8];
         #pragma unroll
@@ -130,17 +142,25 @@ __global__ void k_gn_apply(const __half* __restrict__ x, __half* __restrict__ y,
             o[k] = __float2half_rn(v);
         }
         *reinterpret_cast<uint4*>(y + base + (size_t)p * C) = *reinterpret_cast<const uint4*>(o);
+    };
+    int p = p0 + pl;
+    for (; p + 3 * PL < p1; p += 4 * PL) {                 // 4 loads in flight per thread (see k_gn_stats)
+        uint4 raw[4];
+        #pragma unroll
+        for (int u = 0; u < 4; u++) raw[u] = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)(p + u * PL) * C));
+        #pragma unroll
+        for (int u = 0; u < 4; u++) one(raw[u], p + u * PL);
     }
+    for (; p < p1; p += PL) one(__ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C)), p);
 }
 
 // GroupNorm(+SiLU) backward, pass 1: per-(n,group) sums of dg = dz*gamma and dg*xhat (dz = dy * silu'(z) when do_silu)
 __global__ void k_gn_bwd_stats(const __half* __restrict__ x, const __half* __restrict__ dy, const double* __restrict__ stats,
                                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G, float eps, int do_silu,
                                int pix_per_cta, double* __restrict__ bstats /*[N][G][2]*/) {
-    extern __shared__ float sm[];                 // [C][2] then group constants
+    extern __shared__ float sm[];                 // [PL][C][2], folded in a fixed order
     __shared__ float sm_mean[64], sm_rstd[64];
     const int n = blockIdx.y, cpg = C / G, VPP = C / 8, PL = blockDim.x / VPP;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
     gn_group_consts(stats, n, G, (double)HW * cpg, eps, sm_mean, sm_rstd);
     __syncthreads();
     const int pl = threadIdx.x / VPP, cv = threadIdx.x % VPP;
@@ -153,9 +173,7 @@ __global__ void k_gn_bwd_stats(const __half* __restrict__ x, const __half* __res
         }
         const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
         const size_t base = ((size_t)n * HW) * C + (size_t)cv * 8;
-        for (int p = p0 + pl; p < p1; p += PL) {
-            const uint4 rx = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
-            const uint4 rd = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C));
+        auto one = [&](const uint4& rx, const uint4& rd) {
             const __half* hx = reinterpret_cast<const __half*>(&rx); const __half* hd = reinterpret_cast<const __half*>(&rd);
             #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -165,14 +183,23 @@ __global__ void k_gn_bwd_stats(const __half* __restrict__ x, const __half* __res
                 const float dg = d * ga[k];
                 s1[k] += dg; s2[k] = fmaf(dg, xh, s2[k]);
             }
+        };
+        int p = p0 + pl;
+        for (; p + PL < p1; p += 2 * PL) {                 // 4 loads in flight per thread
+            const uint4 rx0 = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C)), rd0 = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C));
+            const uint4 rx1 = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)(p + PL) * C)), rd1 = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)(p + PL) * C));
+            one(rx0, rd0); one(rx1, rd1);
         }
+        for (; p < p1; p += PL)
+            one(__ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C)), __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C)));
         #pragma unroll
-        for (int k = 0; k < 8; k++) { atomicAdd(&sm[2 * (cv * 8 + k)], s1[k]); atomicAdd(&sm[2 * (cv * 8 + k) + 1], s2[k]); }
+        for (int k = 0; k < 8; k++) { sm[2 * (pl * C + cv * 8 + k)] = s1[k]; sm[2 * (pl * C + cv * 8 + k) + 1] = s2[k]; }
     }
     __syncthreads();
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double a = 0, b = 0;
-        for (int c = g * cpg; c < (g + 1) * cpg; c++) { a += sm[2 * c]; b += sm[2 * c + 1]; }
+        for (int c = g * cpg; c < (g + 1) * cpg; c++)
+            for (int q = 0; q < PL; q++) { a += sm[2 * (q * C + c)]; b += sm[2 * (q * C + c) + 1]; }
         atomicAdd(&bstats[((size_t)n * G + g) * 2], a); atomicAdd(&bstats[((size_t)n * G + g) * 2 + 1], b);
     }
 }
@@ -198,11 +225,7 @@ __global__ void k_gn_bwd_apply(const __half* __restrict__ x, const __half* __res
     }
     const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
     const size_t base = ((size_t)n * HW) * C + (size_t)cv * 8;
-    for (int p = p0 + pl; p < p1; p += PL) {
-        const uint4 rx = __ldg(reinterpret_cast<const uint4*>(x + base + (size_t)p * C));
-        const uint4 rd = __ldg(reinterpret_cast<const uint4*>(dy + base + (size_t)p * C));
-        uint4 ra = make_uint4(0, 0, 0, 0);
-        if (add) ra = __ldg(reinterpret_cast<const uint4*>(add + base + (size_t)p * C));
+    auto one = [&](const uint4& rx, const uint4& rd, const uint4& ra, int p) {
         const __half* hx = reinterpret_cast<const __half*>(&rx); const __half* hd = reinterpret_cast<const __half*>(&rd);
         const __half* ha = reinterpret_cast<const __half*>(&ra);
         __align__(16) __half o[8];
@@ -217,6 +240,19 @@ __global__ void k_gn_bwd_apply(const __half* __restrict__ x, const __half* __res
             o[k] = __float2half_rn(v);
         }
         *reinterpret_cast<uint4*>(dx + base + (size_t)p * C) = *reinterpret_cast<const uint4*>(o);
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    int p = p0 + pl;
+    for (; p + PL < p1; p += 2 * PL) {                     // 4-6 loads in flight per thread
+        const size_t o0 = base + (size_t)p * C, o1 = base + (size_t)(p + PL) * C;
+        const uint4 rx0 = __ldg(reinterpret_cast<const uint4*>(x + o0)), rd0 = __ldg(reinterpret_cast<const uint4*>(dy + o0));
+        const uint4 rx1 = __ldg(reinterpret_cast<const uint4*>(x + o1)), rd1 = __ldg(reinterpret_cast<const uint4*>(dy + o1));
+        const uint4 ra0 = add ? __ldg(reinterpret_cast<const uint4*>(add + o0)) : zero4, ra1 = add ? __ldg(reinterpret_cast<const uint4*>(add + o1)) : zero4;
+        one(rx0, rd0, ra0, p); one(rx1, rd1, ra1, p + PL);
+    }
+    for (; p < p1; p += PL) {
+        const size_t o0 = base + (size_t)p * C;
+        one(__ldg(reinterpret_cast<const uint4*>(x + o0)), __ldg(reinterpret_cast<const uint4*>(dy + o0)), add ? __ldg(reinterpret_cast<const uint4*>(add + o0)) : zero4, p);
     }
 }
 

@@ -196,12 +196,24 @@ class _EncodeImgs(torch.autograd.Function):
 
 class StableDiffusion(nn.Module):
     def __init__(self, device, sd_version='2.0', hf_key=None, step_range=[0.2, 0.6], unet_cfg=None, vae_cfg=None, seed=0,
-                 unet_state=None, vae_state=None, graph_replay=True):
+                 unet_state=None, vae_state=None, graph_replay=True, defer_backward=False):
         super().__init__()
+        # defer_backward (additive option, default off = the reference's behaviour): train_step does not call latents.backward
+        # itself (nerf/sd.py:171) but returns the surrogate loss  sum(stopgrad(dL/d pred_rgb) * pred_rgb), whose gradient w.r.t.
+        # pred_rgb IS the SDS gradient.  The Trainer adds it to its regularisers and its single loss.backward() (nerf/utils.py:983)
+        # then walks the render graph ONCE instead of twice (the reference back-propagates through the retained render graph a
+        # second time).  Parameter gradients are identical (linearity); only the returned loss value differs (0 in the reference).
+        self.defer_backward = bool(defer_backward)
         self.device = torch.device(device)
         self.sd_version = sd_version
-        if sd_version != '2.0' and unet_cfg is None:
-            raise ValueError(f'Stable-diffusion version {sd_version} not built (reference default is 2.0, nerf/sd.py:33-34)')
+        # nerf/sd.py:29-37: '2.1' / '2.0' select stable-diffusion-2-1-base / 2-base, hf_key any other checkpoint (BASELINE config 4 names
+        # SD-2.1-768).  All SD-2.x U-Nets share ONE topology (block_out 320/640/1280/1280, head_dim 64, cross dim 1024, linear
+        # projections) and nerf/sd.py:124 always feeds 512x512 -> 64x64 latents, so they all run on the same engine plan; the 768
+        # checkpoint's v-prediction output is consumed as if it were epsilon, exactly like the reference does (it never reads
+        # prediction_type, nerf/sd.py:146-151).  SD-1.5 (cross dim 768, conv projections, 8 heads) is not built.
+        if sd_version not in ('2.0', '2.1') and hf_key is None and unet_cfg is None:
+            raise ValueError(f'Stable-diffusion version {sd_version} not built (2.0 / 2.1 / hf_key of an SD-2.x checkpoint; reference default 2.0, nerf/sd.py:33-34)')
+        self.hf_key = hf_key
         self.unet_cfg = unet_cfg or sd20_unet_cfg()
         self.vae_cfg = vae_cfg or sd_vae_cfg()
         self.engine = SDEngine(self.unet_cfg, self.vae_cfg, self.device, graph_replay=graph_replay)
@@ -281,6 +293,26 @@ class StableDiffusion(nn.Module):
         else:
             t_host = int(t)
         self._t.fill_(t_host)
+        if self.defer_backward:
+            if not islarge and (t_host / self.num_train_timesteps) <= 0.4:
+                return 0, None
+            with torch.no_grad():
+                hw = self.vae_cfg["image_hw"] // 8
+                eps = L.f32c(eps_posterior) if eps_posterior is not None else torch.randn(1, 4, hw, hw, device=self.device)
+                rgb = L.f32c(pred_rgb.detach())
+                H, W = rgb.shape[-2:]
+                latents = torch.empty(1, 4, hw, hw, dtype=torch.float32, device=rgb.device)
+                grad_rgb = torch.empty_like(rgb)
+                if noise is None:
+                    noise = torch.randn_like(latents)
+                with self.engine.on_stream():
+                    L.check(L.lib().mi3d_sd_encode(self.engine.h, L.ptr(rgb), C.c_int(H), C.c_int(W), L.ptr(eps), L.ptr(latents), L.stream()), "sd_encode")
+                noise_pred, grad = self.unet_sds(latents, noise, self._t, text_embeddings, guidance_scale)
+                with self.engine.on_stream():
+                    L.check(L.lib().mi3d_sd_encode_backward(self.engine.h, L.ptr(grad), L.ptr(eps), C.c_int(H), C.c_int(W), L.ptr(grad_rgb), L.stream()),
+                            "sd_encode_backward")
+            self.last = dict(latents=latents, noise_pred=noise_pred, grad=grad, t=t_host)
+            return (grad_rgb * pred_rgb).sum(), None
         latents = self.encode_imgs(pred_rgb, eps_posterior)
         if noise is None:
             noise = torch.randn_like(latents)

@@ -257,3 +257,57 @@ def test_march_overflow_exposes_only_written_rows():
     kw2 = dict(kw, depth_scale=_cu(sc[:n_fit])[None], noises=_cu(noises[:n_fit]))
     ref = net2.render(_cu(ro[:n_fit])[None], _cu(rd[:n_fit])[None], **kw2)
     assert torch.equal(ref["image"][0], out["image"][0][:n_fit])
+
+
+def test_benchmark_size_render_matches_oracle_golden_128():
+    """BASELINE size (128x128 rays, max_steps 512, k = 13, lambertian): image / depth / weights_sum / per-ray sample counts and the
+    orientation mean against tests/golden/render_128.npz, computed once by the CPU oracle (tests/golden/make_golden_128.py; the
+    oracle itself is pinned to the reference's Python by the 24x24 fixtures above)."""
+    from helpers import camera_rays
+    g = load_golden("render_albedo.npz")
+    z = load_golden("render_128.npz")
+    net = _net_from_golden(g)
+    net.train()
+    net.density_bitfield = _cu(sphere_bitfield(float(z["radius"])))
+    ro, rd, sc = camera_rays(128)
+    out = net.render(_cu(ro)[None], _cu(rd)[None], depth_scale=_cu(sc)[None], bg_color=_cu(z["bg_color"]), perturb=True, light_d=_cu(z["light_d"]),
+                     ambient_ratio=float(z["ratio"]), shading="lambertian", force_all_rays=True, max_steps=512, noises=_cu(z["noises"]))
+    ws = list(net._workspaces.values())[0]
+    assert int(ws.counter[0]) == int(z["total"]) == 424346
+    np.testing.assert_array_equal(ws.rays.cpu().numpy()[:, 2], z["counts"])
+    assert max_abs(out["image"][0].detach().cpu(), z["image"]) < 5e-5
+    assert max_abs(out["weights_sum"][0].detach().cpu(), z["weights_sum"]) < 2e-5
+    assert rel_err(out["depth"][0, :, 0].detach().cpu(), z["depth"], floor=1e-2) < 1e-4
+    # loss_orient = sum / padded rows (raymarching.py:237-241 padding applies to the whole image's sample list)
+    m_pad = int(z["total"]) + 128 - int(z["total"]) % 128
+    assert abs(out["loss_orient"].item() / (float(z["sum_orient"]) / m_pad) - 1) < 1e-3
+
+
+def test_update_extra_state_matches_reference_golden():
+    """Row R6 against the REFERENCE's own NeRFRenderer.update_extra_state (renderer.py:587-637) run through the import shims
+    (tests/golden/make_golden_r6.py -> density_r6.npz): EMA-max grid, cells < 0 left alone, mean density, packed bitfield.  The
+    reference's cell jitter (torch.rand_like after manual_seed) is regenerated here and re-ordered from its meshgrid order to the
+    Morton order mi3d_density_grid_update indexes jitter by."""
+    g = load_golden("render_albedo.npz")
+    z = load_golden("density_r6.npz")
+    net = _net_from_golden(g)
+    H = 128
+    grid0 = (np.random.default_rng(int(z["grid0_seed"])).random((1, H ** 3), dtype=np.float32) * 2).astype(np.float32)
+    grid0[0, ::97] = -1.0
+    net.density_grid.copy_(_cu(grid0))
+    torch.manual_seed(int(z["seed"]))
+    j_ref = torch.rand(H ** 3, 3).numpy()                                     # row i = (x, y, z) in meshgrid('ij') order
+    idx = np.arange(H, dtype=np.int32)
+    xx, yy, zz = np.meshgrid(idx, idx, idx, indexing="ij")
+    morton = orm.morton3D(np.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], 1))
+    jitter = np.empty_like(j_ref)
+    jitter[morton] = j_ref
+    net.update_extra_state(decay=0.95, jitter=_cu(jitter[None]))
+    got = net.density_grid[0].cpu().numpy()
+    sub = z["sub"]
+    assert rel_err(got[sub], z["sub_vals"], floor=1e-3) < 5e-5
+    assert np.all(got[::97] == -1.0)
+    assert abs(float(net.mean_density) / float(z["mean_density"]) - 1) < 1e-5
+    bits = net.density_bitfield.cpu().numpy()
+    diff = np.unpackbits(bits ^ z["bitfield"]).sum()
+    assert diff <= 2, diff            # a cell sitting on the threshold (mean density, 4.7358) may flip with the last bit of sigma

@@ -181,3 +181,22 @@ def test_sd_oracle_vs_diffusers_fixtures():
     np.testing.assert_allclose(mean.numpy(), z["out.mean"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(logvar.numpy(), z["out.logvar"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(sd_ref.alphas_cumprod().numpy(), z["out.alphas_cumprod"], rtol=1e-6)
+
+
+def test_adan_oracle_matches_reference_optimizer_vectors():
+    """oracle/adan_ref.py vs tests/golden/adan.npz (recorded from /root/reference/optimizer.py + clip_grad_norm_, 4 steps covering
+    no clip / Adan's 5.0 clip only / both clips): parameters and all four state tensors after every step."""
+    from oracle.adan_ref import AdanRef
+    z = load_golden("adan.npz")
+    params = [torch.from_numpy(z[f"p0_{i}"].copy()) for i in range(4)]
+    lr = float(z["lr"])
+    opt = AdanRef([{"params": params[:1], "lr": lr * 10}, {"params": params[1:], "lr": lr}], eps=1e-8, weight_decay=2e-5, max_grad_norm=5.0,
+                  clip_grad_norm=10.0)
+    for step in range(4):
+        grads = [torch.from_numpy(z[f"g{step}_{i}"].copy()) for i in range(4)]
+        opt.step([grads[:1], grads[1:]])
+        for i, p in enumerate(params):
+            np.testing.assert_allclose(p.numpy(), z[f"p{step + 1}_{i}"], rtol=2e-6, atol=2e-8)
+            for k in ("exp_avg", "exp_avg_sq", "exp_avg_diff", "neg_pre_grad"):
+                ref = z[f"{k}{step + 1}_{i}"]        # differences of gradients cancel: tolerance relative to the tensor's scale
+                np.testing.assert_allclose(opt.state[id(p)][k].numpy(), ref, rtol=2e-6, atol=2e-6 * float(np.abs(ref).max()))

@@ -140,3 +140,29 @@ def test_graph_replay_is_bit_identical_to_plain_launches(tiny):
         for a, b in zip(got, want):
             assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()), call
     assert g.engine.graph_replays() == 3 and plain.engine.graph_replays() == 0
+
+
+def test_deferred_sds_backward_gives_the_same_gradient(tiny):
+    """defer_backward=True: train_step returns the surrogate loss sum(stopgrad(g) * pred_rgb) instead of calling latents.backward
+    itself (nerf/sd.py:171); after loss.backward() pred_rgb.grad equals what the reference-style immediate backward leaves there."""
+    sdm, g, unet, vae = tiny
+    gen = torch.Generator().manual_seed(5)
+    rgb = torch.rand(1, 3, 64, 64, generator=gen).cuda()
+    ctx = torch.randn(2, 77, 128, generator=gen).cuda()
+    eps = torch.randn(1, 4, 32, 32, generator=gen).cuda()
+    noise = torch.randn(1, 4, 32, 32, generator=gen).cuda()
+    a = rgb.clone().requires_grad_()
+    loss, _ = g.train_step(ctx, a, islarge=True, guidance_scale=10, t=450, eps_posterior=eps, noise=noise)
+    assert loss == 0
+    g.defer_backward = True
+    try:
+        b = rgb.clone().requires_grad_()
+        loss, imgs = g.train_step(ctx, b, islarge=True, guidance_scale=10, t=450, eps_posterior=eps, noise=noise)
+        assert imgs is None and torch.is_tensor(loss) and b.grad is None
+        (loss + 0.0).backward()
+        z = rgb.clone().requires_grad_()
+        l0, _ = g.train_step(ctx, z, islarge=False, t=300)
+        assert l0 == 0 and z.grad is None
+    finally:
+        g.defer_backward = False
+    assert float((a.grad - b.grad).abs().max()) <= 1e-5 * float(a.grad.abs().max())
