@@ -150,8 +150,10 @@ typedef struct { const float *w1, *b1, *w2, *b2, *w3, *b3; } mi3d_mlp;
 typedef struct { float *w1, *b1, *w2, *b2, *w3, *b3; } mi3d_mlp_grad;
 
 enum { MI3D_SHADING_ALBEDO = 0, MI3D_SHADING_LAMBERTIAN = 1, MI3D_SHADING_TEXTURELESS = 2, MI3D_SHADING_NORMAL = 3 };
-/* kernel family of the fused field: tcgen05 split-precision tiles (default) or the register-tiled fp32 FFMA kernels */
-enum { MI3D_FIELD_IMPL_TCGEN05 = 0, MI3D_FIELD_IMPL_FFMA = 1 };
+/* kernel family of the fused field.  TCGEN05 (default): tcgen05 split-precision tiles; the backward chain kernel issues the
+ * table-gradient REDs itself (LSU-bound RED stream under the latency-bound MMA chain; = _FUSED_SCATTER).  _SPLIT_SCATTER: the
+ * round-1 pipeline with a separate full-occupancy scatter kernel (A/B arm).  FFMA = the register-tiled fp32 kernels. */
+enum { MI3D_FIELD_IMPL_TCGEN05 = 0, MI3D_FIELD_IMPL_FFMA = 1, MI3D_FIELD_IMPL_TCGEN05_FUSED_SCATTER = 2, MI3D_FIELD_IMPL_TCGEN05_SPLIT_SCATTER = 3 };
 
 typedef struct {
     float bound;          /* opt.bound */
@@ -294,6 +296,34 @@ int mi3d_render_backward(const mi3d_render_args* args, const float* table, const
                          const float* grad_weights_sum, const float* grad_loss_orient, const float* grad_loss_smooth,
                          float* grad_table, const mi3d_mlp_grad* grad_mlp, void* bwd_workspace, int enc_cache_valid,
                          mi3d_stream_t stream);
+
+/* Evaluation renderer: the alive-ray loop of NeRFRenderer.run_cuda's non-training branch (nerf/renderer.py:526-551:
+ * march_rays -> field -> composite_rays until every ray is terminated or max_steps is reached) in ONE call, all loop state on the
+ * device (no per-iteration host synchronisation; the reference compacts the alive list with a boolean mask every iteration).
+ * Outputs [N], [N], [N,3], [N,3] are (re)initialised inside and carry the background mix / depth fix-up of renderer.py:553-570.
+ * done_flag_host (nullable): int in pinned, device-accessible HOST memory; lets the host stop enqueueing iterations early. */
+typedef struct {
+    const float* rays_o;          /* [N,3] */
+    const float* rays_d;          /* [N,3] */
+    const float* depth_scale;     /* [N] or NULL */
+    uint32_t N;
+    const uint8_t* density_bitfield;
+    uint32_t C, H;
+    float bound, dt_gamma;
+    uint32_t max_steps;           /* 1024 in the reference's eval calls */
+    float min_near;               /* 0.2 (wrapper default, raymarching.py:34) */
+    const float* aabb;            /* device [6]: aabb_infer */
+    float T_thresh;               /* 1e-4 (renderer.py:483 default passed to composite_rays) */
+    int perturb;                  /* jitter the first march iteration */
+    uint64_t seed;
+    const float* bg_color;        /* device [3] or NULL -> bg_scalar */
+    float bg_scalar;
+    float max_depth;
+} mi3d_render_eval_args;
+size_t mi3d_render_eval_workspace_bytes(uint32_t N);
+int mi3d_render_eval(const mi3d_render_eval_args* args, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp,
+                     const mi3d_field_cfg* cfg, void* workspace, int* done_flag_host, float* weights_sum, float* depth, float* image,
+                     float* normal, mi3d_stream_t stream);
 
 /* Replaces NeRFRenderer.update_extra_state (nerf/renderer.py:587-637): density_grid [C,H^3] EMA-max update from the
  * field at jittered cell centres, mean density (device scalar out), bitfield repack.  jitter: [C,H^3,3] U[0,1) or NULL

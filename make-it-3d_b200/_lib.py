@@ -70,6 +70,13 @@ class RenderArgs(C.Structure):
                 ("pad_view_mask", C.c_uint32)]
 
 
+class RenderEvalArgs(C.Structure):
+    _fields_ = [("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("depth_scale", C.c_void_p), ("N", C.c_uint32), ("density_bitfield", C.c_void_p),
+                ("C", C.c_uint32), ("H", C.c_uint32), ("bound", C.c_float), ("dt_gamma", C.c_float), ("max_steps", C.c_uint32), ("min_near", C.c_float),
+                ("aabb", C.c_void_p), ("T_thresh", C.c_float), ("perturb", C.c_int), ("seed", C.c_uint64), ("bg_color", C.c_void_p),
+                ("bg_scalar", C.c_float), ("max_depth", C.c_float)]
+
+
 class RenderWs(C.Structure):
     _fields_ = [("N", C.c_uint32), ("cap", C.c_uint32), ("n_views", C.c_uint32)] + \
                [(n, C.c_void_p) for n in ("xyzs", "dirs", "deltas", "sigmas", "rgbs", "tape", "g_sigmas", "g_rgbs", "rays", "counter", "nears",
@@ -80,7 +87,7 @@ class RenderWs(C.Structure):
 RENDER_PHASE_MARCH, RENDER_PHASE_SHADE, RENDER_PHASE_ALL = 1, 2, 3
 
 SHADING = {"albedo": 0, "lambertian": 1, "textureless": 2, "normal": 3}
-FIELD_IMPL = {"tcgen05": 0, "ffma": 1}
+FIELD_IMPL = {"tcgen05": 0, "ffma": 1, "tcgen05_fused_scatter": 2, "tcgen05_split_scatter": 3}
 
 # every symbol include/mi3d.h declares (tests/test_abi.py checks the .so exports exactly these)
 SYMBOLS = [
@@ -91,6 +98,7 @@ SYMBOLS = [
     "mi3d_hashgrid_make", "mi3d_hashgrid_forward", "mi3d_hashgrid_backward",
     "mi3d_field_grid_ctas", "mi3d_field_forward", "mi3d_field_backward", "mi3d_field_backward_workspace_bytes", "mi3d_field_enc_cache_bytes",
     "mi3d_render_workspace_bytes", "mi3d_render_workspace_carve", "mi3d_render_forward", "mi3d_render_backward",
+    "mi3d_render_eval_workspace_bytes", "mi3d_render_eval",
     "mi3d_density_grid_workspace_bytes", "mi3d_density_grid_update", "mi3d_version",
     "mi3d_sumsq_workspace_bytes", "mi3d_sumsq", "mi3d_adan_step",
     "mi3d_gemm_f16", "mi3d_gemm_f16_splitk", "mi3d_flash_attn_f16", "mi3d_conv3x3_f16", "mi3d_tf32_tile_test", "mi3d_gemm_f16_bt",
@@ -123,6 +131,7 @@ def lib():
         _lib.mi3d_field_enc_cache_bytes.restype = C.c_size_t
         _lib.mi3d_render_workspace_bytes.restype = C.c_size_t
         _lib.mi3d_sumsq_workspace_bytes.restype = C.c_size_t
+        _lib.mi3d_render_eval_workspace_bytes.restype = C.c_size_t
         for name in ("mi3d_sd_workspace_bytes", "mi3d_sd_weight_bytes"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_size_t

@@ -966,6 +966,7 @@ struct BwdArgs {
     // split pipeline (encode kernel -> tensor-core chain kernel -> scatter kernel) over tiles [tile0, tile1): see k_bwd_encode
     float* enc_buf; float* denc_buf; uint32_t tile0, tile1;
     const mi3d_view_segs* segs; uint32_t noise_mode;   // multi-view: g_loss_orient / g_loss_smooth are [n_views] arrays
+    float agg_scale_max;                               // fused scatter: warp-aggregate the REDs of levels with scale below this
 };
 
 // d(loss)/d(h) of the 13 evaluations of one sample from the upstream gradients and the forward tape (sigma0, albedo, tap sigmas):
@@ -1296,8 +1297,8 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
     LevelSm* lv = reinterpret_cast<LevelSm*>(w3s + 256);        // 16 * 20 B = 320 B  (ends at 1856)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + oMisc + 2048);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    uint64_t *a1_full = bars, *d1_full = bars + 1, *a2_full = bars + 2, *d2_full = bars + 3, *a3_full = bars + 4, *r3_done = bars + 5,
-             *d3_full = bars + 6, *a4_full = bars + 7, *r4_done = bars + 8, *d4_full = bars + 9;
+    uint64_t *a1_full = bars, *d1_full = bars + 1, *a2_full = bars + 2, *d2_full = bars + 3, *a3_full = bars + 4,
+             *d3_full = bars + 6, *a4_full = bars + 7, *d4_full = bars + 9;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < (oMisc - oE) / 16; i += kThreads) reinterpret_cast<uint4*>(sm + oE)[i] = make_uint4(0, 0, 0, 0);   // zero pads, finite tiles
@@ -1325,8 +1326,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
     if (a.segs && tid < (int)(sizeof(mi3d_view_segs) / 4)) reinterpret_cast<uint32_t*>(&segs_sm)[tid] = reinterpret_cast<const uint32_t*>(a.segs)[tid];
     if (tid == 0) {
         tc::mbar_init(a1_full, 256); tc::mbar_init(d1_full, 1); tc::mbar_init(a2_full, 128); tc::mbar_init(d2_full, 1);
-        tc::mbar_init(a3_full, 128); tc::mbar_init(r3_done, 256); tc::mbar_init(d3_full, 1); tc::mbar_init(a4_full, 128);
-        tc::mbar_init(r4_done, 256); tc::mbar_init(d4_full, 1);
+        tc::mbar_init(a3_full, 128); tc::mbar_init(d3_full, 1); tc::mbar_init(a4_full, 128); tc::mbar_init(d4_full, 1);
         tc::fence_barrier_init();
     }
     if (warp == 12) tc::tmem_alloc(tmem_slot, kTmemCols);
@@ -1351,6 +1351,10 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
         // persistent partial sums over this warp's rows: lane j owns columns j and j+32 of dW3[o][.] ; db3 on lane o
         float aw3[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, ab3 = 0.f;
+        // db2 / db1 = column sums of dZ2 / dZ1 over this warp's rows, same lane <-> column mapping.  (Round 1 had the encoder warps
+        // re-read the dZ tiles from shared memory behind two extra "readers done" barriers; that tied the encoders to the middle of
+        // every evaluation and kept the fused RED scatter from running under the MMA chain.  The owners hold the values in registers.)
+        float ab2[2] = {0.f, 0.f}, ab1[2] = {0.f, 0.f};
         for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
             const RowInfo ri = row_info(R, row);
@@ -1404,7 +1408,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 // ---- epilogue 2: H2 = relu(D2 + b2) ; dZ2 = relu'(H2) * (dO W3) -> A3 ; dW3 / db3 partial sums ----
                 tc::mbar_wait(d2_full, par);
                 tc::tc_fence_after();
-                if (it > 0) { tc::mbar_wait(d4_full, (it - 1) & 1); tc::mbar_wait(r4_done, (it - 1) & 1); }   // A3 free (previous evaluation)
+                if (it > 0) tc::mbar_wait(d4_full, (it - 1) & 1);   // A3 (the dZ tiles) free: the previous evaluation's G1 / WG1 have retired
                 #pragma unroll 1
                 for (int c0 = 0; c0 < D_H; c0 += 32) {
                     uint32_t v[32];
@@ -1427,6 +1431,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                         const uint32_t o = oZ + sw_off16(r, c0 + 8 * q);
                         *reinterpret_cast<uint4*>(sm + o) = ph; *reinterpret_cast<uint4*>(sm + o + kTile) = pm; *reinterpret_cast<uint4*>(sm + o + 2 * kTile) = pl;
                     }
+                    ab2[c0 >> 5] += warp_colsum32(tv, lane);          // db2 (tv is dead after the stores above)
                     // dW3[o][c0 + lane] += sum over this warp's rows of dO[o] * H2[.][c0 + lane]
                     {
                         float t[32];
@@ -1458,7 +1463,6 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 // ---- epilogue 3: dZ1 = relu'(H1) * dH1 -> A3 (after G2 / WG2 retired and the db2 readers are done) ----
                 tc::mbar_wait(d3_full, par);
                 tc::tc_fence_after();
-                tc::mbar_wait(r3_done, par);
                 #pragma unroll 1
                 for (int c0 = 0; c0 < D_H; c0 += 32) {
                     uint32_t v[32];
@@ -1474,6 +1478,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                         const uint32_t o = oZ + sw_off16(r, c0 + 8 * q);
                         *reinterpret_cast<uint4*>(sm + o) = ph; *reinterpret_cast<uint4*>(sm + o + kTile) = pm; *reinterpret_cast<uint4*>(sm + o + 2 * kTile) = pl;
                     }
+                    ab1[c0 >> 5] += warp_colsum32(tv, lane);          // db1
                 }
                 tc::fence_proxy_async();
                 tc::tc_fence_before();
@@ -1484,15 +1489,14 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
         #pragma unroll
         for (int o = 0; o < 4; o++) { atomicAdd(a.g_mlp.w3 + o * D_H + lane, aw3[o][0]); atomicAdd(a.g_mlp.w3 + o * D_H + 32 + lane, aw3[o][1]); }
         if (lane < 4) atomicAdd(a.g_mlp.b3 + lane, ab3);
+        atomicAdd(a.g_mlp.b2 + lane, ab2[0]); atomicAdd(a.g_mlp.b2 + 32 + lane, ab2[1]);
+        atomicAdd(a.g_mlp.b1 + lane, ab1[0]); atomicAdd(a.g_mlp.b1 + 32 + lane, ab1[1]);
     } else if (warp < 12) {
         // ================================ encoders / scatterers ================================
         const int et = tid - 128, r = et & (T - 1), half = et >> 7;
         const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        // column sums for db2 / db1: this thread sums column cj over rows [rs, rs + 32)
-        const int cj = et & 63, rs = (et >> 6) * 32;
         const bool ext = a.enc_buf != nullptr, ext_out = a.denc_buf != nullptr;
-        float ab2 = 0.f, ab1 = 0.f;
         for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
             const RowInfo ri = row_info(R, row);
@@ -1543,32 +1547,6 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     if (ext) load16(a.enc_buf + ((size_t)(tile - a.tile0) * 13 + (e + 1)) * (T * 32) + (size_t)r * 32 + 16 * half, f);
                     else gather16s(a.table, lv, l0, lcount, (pn[0] + a.bound) / inv2b, (pn[1] + a.bound) / inv2b, (pn[2] + a.bound) / inv2b, f);
                 }
-                // db2: column sums of dZ2
-                tc::mbar_wait(a3_full, par);
-                {
-                    float sacc = 0.f;
-                    #pragma unroll 8
-                    for (int rr = 0; rr < 32; rr++) {
-                        const uint32_t o = oZ + sw_off16(rs + rr, cj);
-                        sacc += (__bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o + kTile)))
-                              + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o + 2 * kTile));
-                    }
-                    ab2 += sacc;
-                }
-                mbar_arrive(r3_done);
-                // db1: column sums of dZ1
-                tc::mbar_wait(a4_full, par);
-                {
-                    float sacc = 0.f;
-                    #pragma unroll 8
-                    for (int rr = 0; rr < 32; rr++) {
-                        const uint32_t o = oZ + sw_off16(rs + rr, cj);
-                        sacc += (__bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o)) + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o + kTile)))
-                              + __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sm + o + 2 * kTile));
-                    }
-                    ab1 += sacc;
-                }
-                mbar_arrive(r4_done);
                 // dEnc (this thread's 16 columns of its row) straight from TMEM into registers
                 tc::mbar_wait(d4_full, par);
                 tc::tc_fence_after();
@@ -1589,12 +1567,10 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                     for (int q = 0; q < 8; q++) if (q == i) { g0 = __uint_as_float(g[2 * q]); g1 = __uint_as_float(g[2 * q + 1]); }
                     const LevelSm L = lv[l0 + i];
                     // aggregate where a cell spans several march steps (2 / scale  >  ~1.5 dt_min): levels 0..7 of the reference grid
-                    scatter_level_agg(a.g_table, L, u0, u1, u2, g0, g1, in_range, L.scale < 200.f, lane);
+                    scatter_level_agg(a.g_table, L, u0, u1, u2, g0, g1, in_range, L.scale < a.agg_scale_max, lane);
                 }
             }
         }
-        atomicAdd(a.g_mlp.b2 + cj, ab2);
-        atomicAdd(a.g_mlp.b1 + cj, ab1);
     } else {
         // ================================ MMA issuer ================================
         if (lane == 0) {
@@ -1865,7 +1841,7 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     a.tape = tape; a.g_sigmas = grad_sigmas; a.g_rgbs = grad_rgbs; a.g_normals = grad_normals;
     a.g_loss_orient = grad_loss_orient; a.g_loss_smooth = grad_loss_smooth;
     a.g_table = grad_table; a.g_mlp = *grad_mlp;
-    a.enc_buf = nullptr; a.denc_buf = nullptr; a.tile0 = 0; a.tile1 = 0xFFFFFFFFu;
+    a.enc_buf = nullptr; a.denc_buf = nullptr; a.tile0 = 0; a.tile1 = 0xFFFFFFFFu; a.agg_scale_max = 50.f;
     a.segs = io->segs; a.noise_mode = io->noise_mode;
     if ((io->segs || io->noise_mode) && cfg->impl == MI3D_FIELD_IMPL_FFMA) return MI3D_ERR_ARG;
     if (io->segs && (io->n_views == 0 || io->n_views > MI3D_MAX_VIEWS)) return MI3D_ERR_ARG;
@@ -1881,8 +1857,25 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
                 if (cached && (t0 + kBwdChunkTiles < total_tiles ? t0 + kBwdChunkTiles : total_tiles) <= io->enc_cache_tiles)
                     a.enc_buf = io->enc_cache + (size_t)t0 * 13 * T * 32;   // saved by the forward
                 else { a.enc_buf = enc_tmp; k_bwd_enc_scatter<false><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a); }
-                k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
-                k_bwd_enc_scatter<true><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a);
+                // Where the table-gradient REDs are issued.  Measured at 128x128, M = 424 k (tools/prof_render.py, profiles/r2_scatter_ab.txt):
+                // full 13-evaluation backward 8.2 ms split vs 5.8 ms fused; 7-evaluation backward 3.7 vs 3.4; centre-only (SDS) 0.91 vs 0.89.
+                // The RED stream is LSU-issue-bound (1.29 cycles per lane), the chain is latency-bound: they overlap in one kernel.
+                const bool fuse = cfg->impl != MI3D_FIELD_IMPL_TCGEN05_SPLIT_SCATTER;
+                // inside the chain kernel the 5-step shuffle scans of the warp aggregation compete with the owner warps for issue slots:
+                // aggregate only levels 0-3 (scale < 50, cells >= 7 march steps wide).  Measured (M = 424 k, full backward): threshold 200 ->
+                // 5.79 ms, 120 -> 5.56, 60 -> 5.29, 50 -> 5.36, 25 -> 6.74, no aggregation -> 11.7 (same-address RED serialisation in L2)
+                a.agg_scale_max = 50.f;
+                if (fuse) {
+                    // the chain kernel's encoder warps scatter d(enc) themselves, straight from TMEM: the RED stream (LSU-bound) runs
+                    // under the MMA / epilogue chain (latency-bound) of the next evaluation instead of in a kernel of its own
+                    float* const denc = a.denc_buf;
+                    a.denc_buf = nullptr;
+                    k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
+                    a.denc_buf = denc;
+                } else {
+                    k_field_bwd_tc<<<num_sms(), bwdtc::kThreads, bwdtc::kSmem, (cudaStream_t)stream>>>(a);
+                    k_bwd_enc_scatter<true><<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(a);
+                }
                 if (!io->counter && (uint64_t)(t0 + kBwdChunkTiles) * T >= io->m_fixed) break;
             }
         } else {

@@ -11,8 +11,7 @@
 //     the ray id, i.e. deterministic, unlike the reference's atomicAdd arrival order.
 //   * near/far (slab test) is fused into the march kernel when no precomputed nears/fars are passed.
 //   * the total sample count stays on the device (counter[0]); downstream kernels read it there.
-#include "mi3d_common.cuh"
-#include "../../include/mi3d.h"
+#include "mi3d_internal.cuh"
 
 namespace {
 
@@ -432,7 +431,39 @@ k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* __restr
     normal[3 * (size_t)id] = nx; normal[3 * (size_t)id + 1] = ny; normal[3 * (size_t)id + 2] = nz;
 }
 
+// march_rays (raymarching.cu:907-1014) for the device-controlled evaluation loop (render.cu): n_step samples per alive ray, extents
+// read from the control block; unused slots carry deltas = 0 (the reference zero-fills the buffers every iteration,
+// raymarching.py:399-401; composite_rays stops at dt == 0).  The first-iteration jitter is Philox(seed, ray id).
+__global__ void __launch_bounds__(kRayThreads)
+k_eval_march(const Mi3dEvalCtl* __restrict__ ctl, const int* __restrict__ alive, const float* __restrict__ rays_t, const mi3d_render_eval_args a,
+             const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, int* __restrict__ counter) {
+    const Mi3dEvalCtl c = *ctl;
+    if (c.done) return;
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n == 0) counter[0] = c.rows;
+    if (n >= (uint32_t)c.n_alive) return;
+    const int id = alive[n];
+    RayCtx r;
+    ray_setup(r, a.rays_o + 3 * (size_t)id, a.rays_d + 3 * (size_t)id, a.bound, a.dt_gamma, a.max_steps, a.C, a.H, a.density_bitfield);
+    float t = rays_t[id];
+    if (c.step == 0 && a.perturb)
+        t += mi3d_clampf(t * a.dt_gamma, r.dt_min, r.dt_max) * mi3d_u01(mi3d_philox(make_uint4((uint32_t)id, 0u, 0u, 0x6576616cu), make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32))).x);
+    const size_t base = (size_t)n * c.n_step;
+    const uint32_t k = walk<true>(r, t, fars[id], (uint32_t)c.n_step, xyzs + 3 * base, dirs + 3 * base, deltas + 2 * base);
+    for (uint32_t s = k; s < (uint32_t)c.n_step; s++) {
+        deltas[2 * (base + s)] = 0.f; deltas[2 * (base + s) + 1] = 0.f;
+        #pragma unroll
+        for (int q = 0; q < 3; q++) { xyzs[3 * (base + s) + q] = 0.f; dirs[3 * (base + s) + q] = 0.f; }
+    }
+}
+
 }  // namespace
+
+int mi3d_internal_eval_march(const Mi3dEvalCtl* ctl, const int* alive, const float* rays_t, const mi3d_render_eval_args* a, const float* fars,
+                             float* xyzs, float* dirs, float* deltas, int* counter, cudaStream_t st) {
+    k_eval_march<<<mi3d_ceil_div(a->N, kRayThreads), kRayThreads, 0, st>>>(ctl, alive, rays_t, *a, fars, xyzs, dirs, deltas, counter);
+    MI3D_RETURN_LAUNCH();
+}
 
 extern "C" {
 

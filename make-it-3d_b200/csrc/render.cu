@@ -14,8 +14,7 @@
 // .mean() over the view's 128-padded sample rows) need the view's TOTAL sample count: forward phase MARCH leaves this rank's
 // per-view counts in ws->view_counts, the host all-gathers them (G*G ints over NCCL, no host sync) and passes the table to
 // phase SHADE, which builds the segment table (mi3d_view_segs) the field kernels read.
-#include "mi3d_common.cuh"
-#include "../../include/mi3d.h"
+#include "mi3d_internal.cuh"
 
 namespace {
 
@@ -53,6 +52,97 @@ __global__ void k_view_segments(const int* __restrict__ my_counts, const int* __
     }
     for (uint32_t j = 2 * n_views + 1; j < 2 * MI3D_MAX_VIEWS + 1; j++) s.bounds[j] = run;
     *segs = s;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Evaluation renderer: the alive-ray loop of NeRFRenderer.run_cuda's non-training branch (nerf/renderer.py:526-551)
+// with ALL control state on the device.  The reference iterates on the host: n_alive = rays_alive.shape[0] (a boolean-mask
+// compaction, i.e. a device->host sync per iteration), n_step = clamp(N // n_alive, 1, 8), march -> field -> composite.
+// Here a control block {n_alive, n_step, step, rows, next, done} lives in the workspace; every kernel reads its extent from it,
+// the composite kernel appends surviving rays to the other half of a ping-pong alive list, and a one-thread kernel advances the
+// block.  The host enqueues iterations without ever synchronising; it stops early when it sees the `done` word the advance kernel
+// also writes to a caller-provided pinned / mapped host flag (a stale read only costs a few empty iterations).
+// ---------------------------------------------------------------------------------------------------------
+using EvalCtl = Mi3dEvalCtl;
+
+__global__ void k_eval_init(uint32_t N, const float* __restrict__ nears, int* __restrict__ alive0, float* __restrict__ rays_t,
+                            float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image, float* __restrict__ normal,
+                            EvalCtl* __restrict__ ctl, volatile int* done_host) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n == 0) {
+        EvalCtl c; c.n_alive = (int)N; c.n_step = 1; c.step = 0; c.rows = (int)N; c.next = 0; c.done = N == 0; c.cur = 0; c.pad = 0;
+        *ctl = c;
+        if (done_host) *done_host = c.done;
+    }
+    if (n >= N) return;
+    alive0[n] = (int)n; rays_t[n] = nears[n];
+    weights_sum[n] = 0.f; depth[n] = 0.f;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) { image[3 * (size_t)n + k] = 0.f; normal[3 * (size_t)n + k] = 0.f; }
+}
+
+// composite_rays (raymarching.cu:1024-1115) with normals mapped to (n + 1) / 2 like renderer.py:548; survivors go to the next list
+__global__ void __launch_bounds__(128)
+k_eval_composite(EvalCtl* __restrict__ ctl, const int* __restrict__ alive, int* __restrict__ alive_next, float* __restrict__ rays_t, float T_thresh,
+                 const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ normals, const float* __restrict__ deltas,
+                 float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image, float* __restrict__ normal) {
+    const EvalCtl c = *ctl;
+    if (c.done) return;
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= (uint32_t)c.n_alive) return;
+    const int id = alive[n];
+    const size_t base = (size_t)n * c.n_step;
+    float t = rays_t[id], d = depth[id], ws = weights_sum[id];
+    float r = image[3 * (size_t)id], g = image[3 * (size_t)id + 1], b = image[3 * (size_t)id + 2];
+    float nx = normal[3 * (size_t)id], ny = normal[3 * (size_t)id + 1], nz = normal[3 * (size_t)id + 2];
+    int s = 0;
+    while (s < c.n_step) {
+        const size_t i = base + s;
+        const float dt = deltas[2 * i];
+        if (dt == 0) break;
+        const float alpha = 1.0f - __expf(-sigmas[i] * dt);
+        const float T = 1 - ws;
+        const float w = alpha * T;
+        ws += w;
+        t += deltas[2 * i + 1];
+        d += w * t;
+        r += w * rgbs[3 * i]; g += w * rgbs[3 * i + 1]; b += w * rgbs[3 * i + 2];
+        nx += w * ((normals[3 * i] + 1) / 2); ny += w * ((normals[3 * i + 1] + 1) / 2); nz += w * ((normals[3 * i + 2] + 1) / 2);
+        if (T < T_thresh) break;
+        s++;
+    }
+    if (s >= c.n_step) { rays_t[id] = t; alive_next[atomicAdd(&ctl->next, 1)] = id; }
+    weights_sum[id] = ws; depth[id] = d;
+    image[3 * (size_t)id] = r; image[3 * (size_t)id + 1] = g; image[3 * (size_t)id + 2] = b;
+    normal[3 * (size_t)id] = nx; normal[3 * (size_t)id + 1] = ny; normal[3 * (size_t)id + 2] = nz;
+}
+
+__global__ void k_eval_advance(EvalCtl* __restrict__ ctl, uint32_t N, uint32_t max_steps, volatile int* done_host) {
+    EvalCtl c = *ctl;
+    if (c.done) return;
+    c.step += c.n_step;                                   // renderer.py:551
+    c.n_alive = c.next; c.next = 0; c.cur ^= 1;
+    if (c.n_alive <= 0 || (uint32_t)c.step >= max_steps) { c.done = 1; c.n_alive = 0; c.rows = 0; }
+    else { const int q = (int)N / c.n_alive; c.n_step = q < 1 ? 1 : (q > 8 ? 8 : q); c.rows = c.n_alive * c.n_step; }   // renderer.py:541
+    *ctl = c;
+    if (done_host && c.done) *done_host = 1;
+}
+
+// final background mix (renderer.py:553-570 for the eval branch): image / normal += (1 - ws) * bg ; depth fix-up
+__global__ void k_eval_finish(uint32_t N, const float* __restrict__ bg_color, float bg_scalar, float max_depth, const float* __restrict__ depth_scale,
+                              const float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image, float* __restrict__ normal) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float tr = 1 - weights_sum[n];
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float bgk = bg_color ? bg_color[k] : bg_scalar;
+        image[3 * (size_t)n + k] += tr * bgk; normal[3 * (size_t)n + k] += tr * bgk;
+    }
+    float dd = depth[n] + tr * max_depth;
+    if (depth_scale) dd *= depth_scale[n];
+    depth[n] = dd;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -179,6 +269,54 @@ int mi3d_render_backward(const mi3d_render_args* ra, const float* table, const m
     io.enc_cache_valid = enc_cache_valid ? 1u : 0u;
     return mi3d_field_backward(&io, table, hg, mlp, cfg, ws->tape, ws->g_sigmas, ws->g_rgbs, nullptr, grad_loss_orient, grad_loss_smooth,
                                grad_table, grad_mlp, bwd_workspace, stream);
+}
+
+
+// ---- evaluation renderer: the whole alive-ray loop, no host synchronisation ----
+size_t mi3d_render_eval_workspace_bytes(uint32_t N) {
+    const size_t rows = (size_t)N + 128;                                // n_alive * n_step <= N (n_step = clamp(N / n_alive, 1, 8))
+    size_t b = 256;                                                    // control block
+    b += align_up((size_t)N * 4, 256) * 5;                             // alive x2, rays_t, nears, fars
+    b += align_up(rows * 12, 256) * 4 + align_up(rows * 8, 256) + align_up(rows * 4, 256);   // xyzs, dirs, rgbs, normals | deltas | sigmas
+    b += 256;                                                          // row counter
+    return b;
+}
+
+int mi3d_render_eval(const mi3d_render_eval_args* a, const float* table, const mi3d_hashgrid* hg, const mi3d_mlp* mlp, const mi3d_field_cfg* cfg,
+                     void* workspace, int* done_flag_host, float* weights_sum, float* depth, float* image, float* normal, mi3d_stream_t stream) {
+    if (!a || !table || !hg || !mlp || !cfg || !workspace || !weights_sum || !depth || !image || !normal || !a->rays_o || !a->rays_d || !a->aabb) return MI3D_ERR_ARG;
+    const uint32_t N = a->N;
+    if (N == 0) return MI3D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* p = (char*)workspace;
+    auto take = [&](size_t bytes) { void* q = p; p += align_up(bytes, 256); return q; };
+    const size_t rows = (size_t)N + 128;
+    EvalCtl* ctl = (EvalCtl*)take(256);
+    int* alive[2] = {(int*)take((size_t)N * 4), (int*)take((size_t)N * 4)};
+    float* rays_t = (float*)take((size_t)N * 4); float* nears = (float*)take((size_t)N * 4); float* fars = (float*)take((size_t)N * 4);
+    float* xyzs = (float*)take(rows * 12); float* dirs = (float*)take(rows * 12); float* rgbs = (float*)take(rows * 12); float* normals = (float*)take(rows * 12);
+    float* deltas = (float*)take(rows * 8); float* sigmas = (float*)take(rows * 4);
+    int* counter = (int*)take(256);
+    int r = mi3d_near_far_from_aabb(a->rays_o, a->rays_d, a->aabb, N, a->min_near, nears, fars, stream);
+    if (r) return r;
+    const unsigned blocks = (N + 127) / 128;
+    k_eval_init<<<blocks, 128, 0, st>>>(N, nears, alive[0], rays_t, weights_sum, depth, image, normal, ctl, done_flag_host);
+    mi3d_field_io io{};
+    io.xyzs = xyzs; io.dirs = dirs; io.counter = counter; io.m_fixed = 0; io.align = 128; io.cap = (uint32_t)rows;
+    mi3d_field_cfg fc = *cfg;
+    fc.n_evals = 7;                                        // sigma, colour AND the finite-difference normal (renderer.py:547-548)
+    for (uint32_t it = 0; it < a->max_steps; it++) {
+        if (done_flag_host && *(volatile int*)done_flag_host) break;      // stale reads only cost empty iterations
+        const int cur = (int)(it & 1);
+        r = mi3d_internal_eval_march(ctl, alive[cur], rays_t, a, fars, xyzs, dirs, deltas, counter, st);
+        if (r) return r;
+        r = mi3d_field_forward(&io, table, hg, mlp, &fc, sigmas, rgbs, normals, nullptr, nullptr, nullptr, nullptr, stream);
+        if (r) return r;
+        k_eval_composite<<<blocks, 128, 0, st>>>(ctl, alive[cur], alive[cur ^ 1], rays_t, a->T_thresh, sigmas, rgbs, normals, deltas, weights_sum, depth, image, normal);
+        k_eval_advance<<<1, 1, 0, st>>>(ctl, N, a->max_steps, done_flag_host);
+    }
+    k_eval_finish<<<blocks, 128, 0, st>>>(N, a->bg_color, a->bg_scalar, a->max_depth, a->depth_scale, weights_sum, depth, image, normal);
+    MI3D_RETURN_LAUNCH();
 }
 
 }  // extern "C"

@@ -173,38 +173,15 @@ class NeRFRenderer(nn.Module):
             if light_d is None:                                        # renderer.py:496-499
                 light_d = safe_normalize(rays_o[0] + torch.randn(3, device=device, dtype=torch.float))
             light_d = L.f32c(light_d)
-            nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_infer)
-            dtype = torch.float32
-            weights_sum = torch.zeros(N, dtype=dtype, device=device)
-            depth = torch.zeros(N, dtype=dtype, device=device)
-            image = torch.zeros(N, 3, dtype=dtype, device=device)
-            normal = torch.zeros(N, 3, dtype=dtype, device=device)
-            n_alive = N
-            rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
-            rays_t = nears.clone()
-            step = 0
-            while step < max_steps:                                   # renderer.py:535-551
-                n_alive = rays_alive.shape[0]
-                if n_alive <= 0:
-                    break
-                n_step = max(min(N // n_alive, 8), 1)
-                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
-                                                            self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128,
-                                                            perturb if step == 0 else False, dt_gamma, max_steps)
-                sigmas, rgbs, normals = self(xyzs, dirs, light_d, ratio=ambient_ratio, shading=shading)
-                normals = (normals + 1) / 2
-                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, normals, deltas, weights_sum, depth,
-                                           image, normal, T_thresh)
-                rays_alive = rays_alive[rays_alive >= 0]
-                step += n_step
-            bg = 1 if bg_color is None else bg_color
-            image = (image + (1 - weights_sum).unsqueeze(-1) * bg).view(*prefix, 3)
-            normal = (normal + (1 - weights_sum).unsqueeze(-1) * bg).view(*prefix, 3)
-            depth = depth + (1 - weights_sum) * self.opt.max_depth
-            if depth_scale is not None:
-                depth = depth.view(*prefix, 1) * depth_scale.view(*prefix, 1)
-            else:
+            if kwargs.get('eval_loop', 'device') == 'device':
+                # the whole alive-ray loop in ONE C call, loop state on the device (mi3d_render_eval)
+                weights_sum, depth, image, normal, nears, fars = self._render_eval_device(
+                    rays_o, rays_d, depth_scale, bg_color, dt_gamma, light_d, ambient_ratio, shading, perturb, max_steps, T_thresh)
+                image, normal = image.view(*prefix, 3), normal.view(*prefix, 3)
                 depth = depth.view(*prefix, 1)
+            else:
+                weights_sum, depth, image, normal, nears, fars = self._render_eval_host_loop(
+                    rays_o, rays_d, depth_scale, bg_color, dt_gamma, light_d, ambient_ratio, shading, perturb, max_steps, T_thresh, prefix)
             results['normal'] = normal
 
         results['image'] = image
@@ -212,6 +189,82 @@ class NeRFRenderer(nn.Module):
         results['weights_sum'] = weights_sum.reshape(*prefix)
         results['mask'] = (nears < fars).reshape(*prefix)
         return results
+
+    def _render_eval_host_loop(self, rays_o, rays_d, depth_scale, bg_color, dt_gamma, light_d, ambient_ratio, shading, perturb, max_steps,
+                               T_thresh, prefix):
+        """The reference's host-driven loop (renderer.py:526-551) over the B1 / B2 entry points, one device->host sync per iteration
+        (the boolean-mask compaction).  Kept as the A/B arm of the device-controlled loop (`eval_loop='host'`)."""
+        N, device = rays_o.shape[0], rays_o.device
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_infer)
+        dtype = torch.float32
+        weights_sum = torch.zeros(N, dtype=dtype, device=device)
+        depth = torch.zeros(N, dtype=dtype, device=device)
+        image = torch.zeros(N, 3, dtype=dtype, device=device)
+        normal = torch.zeros(N, 3, dtype=dtype, device=device)
+        n_alive = N
+        rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
+        rays_t = nears.clone()
+        step = 0
+        while step < max_steps:                                   # renderer.py:535-551
+            n_alive = rays_alive.shape[0]
+            if n_alive <= 0:
+                break
+            n_step = max(min(N // n_alive, 8), 1)
+            xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+                                                        self.density_bitfield, self.cascade, self.grid_size, nears, fars, 128,
+                                                        perturb if step == 0 else False, dt_gamma, max_steps)
+            sigmas, rgbs, normals = self(xyzs, dirs, light_d, ratio=ambient_ratio, shading=shading)
+            normals = (normals + 1) / 2
+            raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, normals, deltas, weights_sum, depth,
+                                       image, normal, T_thresh)
+            rays_alive = rays_alive[rays_alive >= 0]
+            step += n_step
+        bg = 1 if bg_color is None else bg_color
+        image = (image + (1 - weights_sum).unsqueeze(-1) * bg).view(*prefix, 3)
+        normal = (normal + (1 - weights_sum).unsqueeze(-1) * bg).view(*prefix, 3)
+        depth = depth + (1 - weights_sum) * self.opt.max_depth
+        if depth_scale is not None:
+            depth = depth.view(*prefix, 1) * depth_scale.view(*prefix, 1)
+        else:
+            depth = depth.view(*prefix, 1)
+        return weights_sum, depth, image, normal, nears, fars
+
+    def _render_eval_device(self, rays_o, rays_d, depth_scale, bg_color, dt_gamma, light_d, ambient_ratio, shading, perturb, max_steps, T_thresh):
+        table, mlp_params, hg, cfg = self._field_handles()
+        N, dev = rays_o.shape[0], rays_o.device
+        lib = L.lib()
+        key = (N, str(dev))
+        if getattr(self, "_eval_ws_key", None) != key:
+            self._eval_ws = torch.empty(lib.mi3d_render_eval_workspace_bytes(C.c_uint32(N)), dtype=torch.uint8, device=dev)
+            self._eval_done = torch.zeros(1, dtype=torch.int32).pin_memory()      # device-written, host-polled (no sync)
+            self._eval_ws_key = key
+        self._eval_done.zero_()
+        cfg = dict(cfg, n_evals=7, shading=shading, ambient_ratio=float(ambient_ratio))
+        cf = field_ops._cfg_struct(cfg, light_d)
+        mlp = field_ops._mlp_struct(mlp_params)
+        if bg_color is not None and not torch.is_tensor(bg_color):
+            bg_color = torch.full((3,), float(bg_color), device=dev)
+        if bg_color is not None:
+            bg_color = L.f32c(bg_color.to(dev))
+        ds = L.f32c(depth_scale).view(-1) if depth_scale is not None else None
+        a = L.RenderEvalArgs()
+        a.rays_o = rays_o.data_ptr(); a.rays_d = rays_d.data_ptr(); a.depth_scale = ds.data_ptr() if ds is not None else None; a.N = N
+        a.density_bitfield = self.density_bitfield.data_ptr(); a.C = self.cascade; a.H = self.grid_size
+        a.bound = float(self.bound); a.dt_gamma = float(dt_gamma); a.max_steps = int(max_steps); a.min_near = 0.2
+        a.aabb = self.aabb_infer.data_ptr(); a.T_thresh = float(T_thresh); a.perturb = 1 if perturb else 0
+        a.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        a.bg_color = bg_color.data_ptr() if bg_color is not None else None; a.bg_scalar = 1.0; a.max_depth = float(self.opt.max_depth)
+        f32 = dict(dtype=torch.float32, device=dev)
+        weights_sum, depth = torch.empty(N, **f32), torch.empty(N, **f32)
+        image, normal = torch.empty(N, 3, **f32), torch.empty(N, 3, **f32)
+        L.check(lib.mi3d_render_eval(C.byref(a), L.ptr(table), C.byref(hg), C.byref(mlp), C.byref(cf), L.ptr(self._eval_ws),
+                                     C.c_void_p(self._eval_done.data_ptr()), L.ptr(weights_sum), L.ptr(depth), L.ptr(image), L.ptr(normal), L.stream()),
+                "render_eval")
+        # nears / fars live at fixed offsets of the workspace (control block 256 B, two alive lists, rays_t, then nears, fars)
+        stride = (N * 4 + 255) // 256 * 256
+        nears = self._eval_ws[256 + 3 * stride:256 + 3 * stride + 4 * N].view(torch.float32)
+        fars = self._eval_ws[256 + 4 * stride:256 + 4 * stride + 4 * N].view(torch.float32)
+        return weights_sum, depth, image, normal, nears, fars
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128, jitter=None, seed=None):
