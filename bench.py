@@ -248,10 +248,10 @@ def run_ours(args):
         if world > 1:
             torch.distributed.destroy_process_group()
         return
-    if args.timeline:
+    def timeline(n_steps):
         # per-rank CUDA-event table of the step phases (profiles/: where a multi-GPU step spends its time on every rank)
         rows = []
-        for s in range(args.steps):
+        for s in range(n_steps):
             if world > 1:
                 torch.distributed.barrier()
             marks = []
@@ -264,14 +264,20 @@ def run_ours(args):
             torch.distributed.all_gather(allt, t)
         else:
             allt = [t]
+        if rank != 0:
+            return None
+        out = {"n_gpus": world, "render_split": args.render_split if world > 1 else "single", "steps": n_steps,
+               "columns": ["render_fwd_ms (incl. its collectives)", "sd_guidance_ms (VAE enc, U-Net, SDS backward to the field)",
+                           "regulariser_backward_ms", "grad_allreduce_ms", "samples_marched_by_rank"],
+               "per_rank": [[[round(float(x), 3) for x in r] for r in a.tolist()] for a in allt]}
+        arr = np.array(out["per_rank"])
+        out["mean_per_rank"] = [[round(float(x), 3) for x in arr[r].mean(0)] for r in range(world)]
+        out["step_ms_max_over_ranks_mean"] = round(float(arr[:, :, :4].sum(2).max(0).mean()), 3)
+        return out
+
+    if args.timeline:
+        out = timeline(args.steps)
         if rank == 0:
-            out = {"n_gpus": world, "render_split": args.render_split if world > 1 else "single", "steps": args.steps,
-                   "columns": ["render_fwd_ms (incl. its collectives)", "sd_guidance_ms (VAE enc, U-Net, SDS backward to the field)",
-                               "regulariser_backward_ms", "grad_allreduce_ms", "samples_marched_by_rank"],
-                   "per_rank": [[[round(float(x), 3) for x in r] for r in a.tolist()] for a in allt]}
-            arr = np.array(out["per_rank"])
-            out["mean_per_rank"] = [[round(float(x), 3) for x in arr[r].mean(0)] for r in range(world)]
-            out["step_ms_max_over_ranks_mean"] = round(float(arr[:, :, :4].sum(2).max(0).mean()), 3)
             print(json.dumps(out))
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -422,7 +428,12 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if args.timeline_out:
+        tl = timeline(8)
+        if rank == 0:
+            with open(args.timeline_out, "w") as f:
+                f.write(json.dumps(tl) + "\n")
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -500,6 +511,7 @@ def main():
                     help="N > 1: 'rays' = ray-parallel render (balanced, default), 'views' = round-1 view-parallel render (A/B)")
     ap.add_argument("--defer-backward", action="store_true",
                     help="StableDiffusion(defer_backward=True): the SDS gradient joins the regularisers in ONE render backward (A/B; off = reference order)")
+    ap.add_argument("--timeline-out", default=None, help="after the timed regions, also write the per-rank phase timeline of a few extra steps to this file")
     ap.add_argument("--timeline", action="store_true",
                     help="print a per-rank CUDA-event table of the step phases instead of the bench line (for profiles/)")
     ap.add_argument("--launch-list", action="store_true",

@@ -411,6 +411,7 @@ typedef struct {
     int layers_per_block;     /* 2 */
     int groups;               /* 32 */
     int image_hw;             /* 512 */
+    int decoder;              /* != 0: also plan the decoder (mi3d_sd_decode; the denoise side branch of nerf/sd.py:153-159) */
 } mi3d_vae_cfg;
 
 typedef struct mi3d_sd* mi3d_sd_t;
@@ -441,6 +442,12 @@ int mi3d_sd_encode_backward(mi3d_sd_t h, const float* grad_latents, const float*
  * text_embeddings fp32 [2,77,cross_dim] (uncond first); noise_pred / grad (nullable) fp32 [1,4,h,w]. */
 int mi3d_sd_unet_sds(mi3d_sd_t h, const float* latents, const float* noise, const long long* t, const float* alphas_cumprod,
                      const float* text_embeddings, float guidance_scale, float* noise_pred, float* grad, mi3d_stream_t stream);
+/* The "denoise" side branch of train_step (nerf/sd.py:153-159), taken on non-large views when t <= 0.4 T:
+ * replaces scheduler.step (DDIM, eta 0, t -> t-1; fp32 [1,4,h,w], n = 4*h*w elements) and decode_latents (nerf/sd.py:201-210:
+ * vae.decode(latents / 0.18215) -> (x/2 + 0.5).clamp(0,1); imgs fp32 [1,3,image_hw,image_hw]).  Forward only, like the reference. */
+int mi3d_sd_ddim_step(const float* noise_pred, const float* latents_noisy, const long long* t, const float* alphas_cumprod,
+                      float* prev_sample, int n, mi3d_stream_t stream);
+int mi3d_sd_decode(mi3d_sd_t h, const float* latents, float* imgs, mi3d_stream_t stream);
 /* live timing of the tensor-core tile kernel: enable=1 starts recording CUDA events around every launch; enable=0 stops and
  * returns the summed kernel time (ms) and launch count (HOST pointers; synchronises on the recorded events). */
 int mi3d_sd_profile(mi3d_sd_t h, int enable, float* gemm_ms_host, int* launches_host);

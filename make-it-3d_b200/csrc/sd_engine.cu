@@ -68,6 +68,7 @@ struct Engine {
     // fixed I/O buffers
     T4 unet_in; float* unet_out = nullptr; __half* ctx16 = nullptr; float* temb = nullptr; long long* t_dev = nullptr;
     T4 vae_in; float* vae_moments = nullptr; float* vae_gmoments = nullptr; __half* vae_gin = nullptr;
+    T4 dec_in; float* dec_out = nullptr; std::vector<Op> dec_ops;          // VAE decoder (denoise side branch, nerf/sd.py:201-210)
     int ctx_pad = 128;
     float* splitk_ws = nullptr; size_t splitk_elems = 0;      // fp32 scratch shared by all split-K GEMMs (they run one at a time)
     // optional live timing of the tensor-core tile kernel (bench.py roofline leg): CUDA events around every k_tc_gemm launch
@@ -622,6 +623,106 @@ struct Engine {
         cur = nullptr;
     }
 
+    // ------------------------------------------------------------------------------------------------------
+    // VAE decoder (diffusers AutoencoderKL.decode: post_quant_conv folded into the API kernel, then Decoder): forward only.
+    // ------------------------------------------------------------------------------------------------------
+    T4 dec_resnet(const std::string& pre, const T4& x, int cout) {
+        const int cin = x.c;
+        T4 a1 = act(x.n, x.h, x.w, cin);
+        groupnorm(x, pre + ".norm1", 1e-6f, 1, a1);
+        T4 h1 = act(x.n, x.h, x.w, cout);
+        conv3(a1, (const __half*)param(pre + ".conv1.weight", {cout, cin, 3, 3}, PK_CONV3).dst, cout, h1, pf(pre + ".conv1.bias", {cout}));
+        T4 a2 = act(x.n, x.h, x.w, cout);
+        groupnorm(h1, pre + ".norm2", 1e-6f, 1, a2);
+        const __half* sc = x.p;
+        if (cin != cout) {
+            T4 sh = act(x.n, x.h, x.w, cout);
+            linear(x.p, x.rows(), cin, (const __half*)param(pre + ".conv_shortcut.weight", {cout, cin, 1, 1}, PK_CONV1).dst, cout, sh.p,
+                   pf(pre + ".conv_shortcut.bias", {cout}));
+            sc = sh.p;
+        }
+        T4 out = act(x.n, x.h, x.w, cout);
+        conv3(a2, (const __half*)param(pre + ".conv2.weight", {cout, cout, 3, 3}, PK_CONV3).dst, cout, out, pf(pre + ".conv2.bias", {cout}), nullptr, sc);
+        return out;
+    }
+
+    void build_vae_dec() {
+        begin_list(&dec_ops);
+        const mi3d_vae_cfg& c = vcfg;
+        const int nlev = c.n_levels, L = c.layers_per_block, hw = c.image_hw >> (nlev - 1);
+        int ch = c.block_out[nlev - 1];
+        dec_in = act(1, hw, hw, 4);                         // post_quant_conv(latents / 0.18215), NHWC fp16, written by the API kernel
+        pf("post_quant_conv.weight", {c.latent_ch, c.latent_ch, 1, 1}); pf("post_quant_conv.bias", {c.latent_ch});
+        T4 h = act(1, hw, hw, ch);
+        {
+            const float* w = (const float*)param("decoder.conv_in.weight", {ch, c.latent_ch, 3, 3}, PK_CONV_F32_OHWI).dst;
+            const float* b = pf("decoder.conv_in.bias", {ch});
+            const T4 xin = dec_in, ho = h; const int co = ch, lc = c.latent_ch;
+            push([=](cudaStream_t st) {
+                if (lc != 4 || co % 8) return (int)MI3D_ERR_ARG;
+                const size_t sm = (size_t)co * 9 * 4 * sizeof(float);
+                if (sm > 100 * 1024) return (int)MI3D_ERR_ARG;
+                sdk::k_conv_small_cin<4><<<small_cin_grid(ho.numel(), sm), 256, sm, st>>>(xin.p, w, b, ho.p, 1, xin.h, xin.w, co);
+                return (int)cudaGetLastError();
+            });
+        }
+        h = dec_resnet("decoder.mid_block.resnets.0", h, ch);
+        {   // single-head attention over all pixels (same construction as the encoder's, no tape)
+            const std::string pre = "decoder.mid_block.attentions.0";
+            const long long M = h.rows(); const int C = ch;
+            T4 n = act(h.n, h.h, h.w, C);
+            groupnorm(h, pre + ".group_norm", 1e-6f, 0, n);
+            __half *q = alloc16(M * C), *k = alloc16(M * C), *v = alloc16(M * C), *vT = alloc16(M * C);
+            linear(n.p, M, C, (const __half*)param(pre + ".to_q.weight", {C, C}, PK_LINEAR).dst, C, q, pf(pre + ".to_q.bias", {C}));
+            linear(n.p, M, C, (const __half*)param(pre + ".to_k.weight", {C, C}, PK_LINEAR).dst, C, k, pf(pre + ".to_k.bias", {C}));
+            linear(n.p, M, C, (const __half*)param(pre + ".to_v.weight", {C, C}, PK_LINEAR).dst, C, v, pf(pre + ".to_v.bias", {C}));
+            transpose(v, vT, 1, (int)M, C);
+            __half* P = alloc16((size_t)M * M);
+            { Mat qa{q, C, M, C}; Mat kb{k, C, M, C}; Out oo; oo.p16 = P; oo.ldc = M; Epi e; gemm(qa, kb, (int)M, oo, e); }
+            softmax(P, (size_t)M, (int)M, (int)M, 1.0f / sqrtf((float)C));
+            __half* ao = alloc16(M * C);
+            { Mat pa{P, M, M, (int)M}; Mat vb{vT, M, C, (int)M}; Out oo; oo.p16 = ao; oo.ldc = C; Epi e; gemm(pa, vb, C, oo, e); }
+            T4 out = act(h.n, h.h, h.w, C);
+            linear(ao, M, C, (const __half*)param(pre + ".to_out.0.weight", {C, C}, PK_LINEAR).dst, C, out.p, pf(pre + ".to_out.0.bias", {C}), h.p);
+            h = out;
+        }
+        h = dec_resnet("decoder.mid_block.resnets.1", h, ch);
+        for (int i = 0; i < nlev; i++) {
+            const int co = c.block_out[nlev - 1 - i];
+            for (int j = 0; j < L + 1; j++) h = dec_resnet("decoder.up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), h, co);
+            ch = co;
+            if (i < nlev - 1) {
+                T4 up = act(h.n, h.h * 2, h.w * 2, h.c);
+                const T4 hh = h;
+                push([=](cudaStream_t st) {
+                    sdk::k_upsample2x<<<blocks_for(up.numel() / 8), 256, 0, st>>>(hh.p, up.p, hh.n, hh.h, hh.w, hh.c);
+                    return (int)cudaGetLastError();
+                });
+                T4 y = act(up.n, up.h, up.w, up.c);
+                const std::string up_pre = "decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv";
+                conv3(up, (const __half*)param(up_pre + ".weight", {h.c, h.c, 3, 3}, PK_CONV3).dst, h.c, y, pf(up_pre + ".bias", {h.c}));
+                h = y;
+            }
+        }
+        T4 a = act(h.n, h.h, h.w, h.c);
+        groupnorm(h, "decoder.conv_norm_out", 1e-6f, 1, a);
+        dec_out = alloc32((size_t)a.rows() * 4);
+        {
+            // conv_out ch -> 3: the 4-output direct kernel; its 4th weight row / bias entry is the (zeroed) pad allocated right behind
+            const __half* w = (const __half*)param("decoder.conv_out.weight", {c.in_ch, ch, 3, 3}, PK_CONV_SMALL_COUT).dst;
+            alloc16((size_t)9 * ch);
+            const float* b = pf("decoder.conv_out.bias", {c.in_ch});
+            alloc32(4);
+            float* o = dec_out; const int ic = c.in_ch;
+            push([=](cudaStream_t st) {
+                if (ic != 3) return (int)MI3D_ERR_ARG;
+                sdk::k_conv_small_cout<4><<<small_cout_grid((size_t)a.rows(), a.c), 256, (size_t)4 * 9 * a.c * 2, st>>>(a.p, w, b, o, a.n, a.h, a.w, a.c);
+                return (int)cudaGetLastError();
+            });
+        }
+        cur = nullptr;
+    }
+
     // dgrad of a stride-1 3x3 conv: dx = conv3(dy, W_flipped^T)  (+ residual accumulation)
     void conv3_dgrad(const T4& dy, const std::string& wname, int cin, const T4& dx, const __half* add = nullptr) {
         Param& w = params[pindex[wname]];
@@ -739,11 +840,11 @@ struct Engine {
     float* vae_grad_img = nullptr;
 
     int build(bool dry_run) {
-        dry = dry_run; off = 0; err = 0; params.clear(); pindex.clear(); unet_ops.clear(); enc_ops.clear(); enc_bwd_ops.clear();
+        dry = dry_run; off = 0; err = 0; params.clear(); pindex.clear(); unet_ops.clear(); enc_ops.clear(); enc_bwd_ops.clear(); dec_ops.clear();
         vres.clear(); vdown.clear(); vorder.clear(); named.clear();
         splitk_elems = (size_t)2048 * 2560; splitk_ws = alloc32(splitk_elems);       // covers M <= 2048 rows x N <= 2560
         if (ucfg.n_levels > 0) build_unet();
-        if (vcfg.n_levels > 0) { build_vae(); build_vae_bwd(); }
+        if (vcfg.n_levels > 0) { build_vae(); build_vae_bwd(); if (vcfg.decoder) build_vae_dec(); }
         return err;
     }
 
@@ -782,6 +883,39 @@ struct Engine {
 // ------------------------------------------------------------------------------------------------------------
 // API-level elementwise kernels (latent arithmetic of nerf/sd.py:124-171)
 // ------------------------------------------------------------------------------------------------------------
+// DDIMScheduler.step, eta = 0, after set_timesteps(num_train_timesteps) (nerf/sd.py:154-155): prev = t - 1, alpha_prev = alphas[max(t-1, 0)]
+// (set_alpha_to_one = False).  x0 = (x_t - sqrt(1 - a_t) eps) / sqrt(a_t);  x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps
+__global__ void k_ddim_step(const float* __restrict__ noise_pred, const float* __restrict__ latents_noisy, const float* __restrict__ alphas,
+                            const long long* __restrict__ t, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long tt = *t;
+    const float a_t = alphas[tt], a_p = alphas[tt > 0 ? tt - 1 : 0];
+    const float x0 = (latents_noisy[i] - sqrtf(1.f - a_t) * noise_pred[i]) / sqrtf(a_t);
+    out[i] = sqrtf(a_p) * x0 + sqrtf(1.f - a_p) * noise_pred[i];
+}
+
+// decoder input: z = post_quant_conv(latents / 0.18215) (1x1 conv, 4 -> 4), latents fp32 NCHW [1,4,h,w] -> NHWC fp16 [pix][4]
+__global__ void k_dec_in(const float* __restrict__ latents, const float* __restrict__ w, const float* __restrict__ b, __half* __restrict__ out, int pix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pix) return;
+    float x[4];
+    #pragma unroll
+    for (int c = 0; c < 4; c++) x[c] = latents[(size_t)c * pix + i] / 0.18215f;
+    __align__(8) __half o[4];
+    #pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = __float2half_rn(b[k] + w[4 * k] * x[0] + w[4 * k + 1] * x[1] + w[4 * k + 2] * x[2] + w[4 * k + 3] * x[3]);
+    *reinterpret_cast<uint2*>(out + 4 * (size_t)i) = *reinterpret_cast<const uint2*>(o);
+}
+
+// imgs = (decoder_out / 2 + 0.5).clamp(0, 1) (nerf/sd.py:208), [pix][4] fp32 -> NCHW fp32 [1,3,S,S]
+__global__ void k_dec_out(const float* __restrict__ o, float* __restrict__ imgs, int pix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pix) return;
+    #pragma unroll
+    for (int c = 0; c < 3; c++) imgs[(size_t)c * pix + i] = fminf(fmaxf(o[4 * (size_t)i + c] / 2.f + 0.5f, 0.f), 1.f);
+}
+
 // bilinear resize (align_corners=False, F.interpolate semantics) of pred_rgb [3,H,W] fp32 NCHW to S x S, then 2x-1, NHWC fp16 (4 ch)
 __global__ void k_interp_in(const float* __restrict__ rgb, int H, int W, __half* __restrict__ out, int S) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1084,6 +1218,26 @@ int mi3d_sd_encode_backward(mi3d_sd_t h, const float* grad_latents, const float*
     sd::k_sample_latents_bwd<<<(pix + 127) / 128, 128, 0, st>>>(e.vae_moments, qw, qb, eps_posterior, grad_latents, e.vae_gmoments, pix);
     int r = e.run(e.enc_bwd_ops, st); if (r) return r;
     sd::k_interp_bwd<<<(H * W + 127) / 128, 128, 0, st>>>(e.vae_grad_img, S, grad_pred_rgb, H, W);
+    return (int)cudaGetLastError();
+}
+
+// nerf/sd.py:154-155: one DDIM step t -> t-1 on the noisy latents with the CFG-combined noise prediction.  All fp32 [1,4,h,w].
+int mi3d_sd_ddim_step(const float* noise_pred, const float* latents_noisy, const long long* t, const float* alphas_cumprod, float* prev_sample,
+                      int n, mi3d_stream_t stream) {
+    if (!noise_pred || !latents_noisy || !t || !alphas_cumprod || !prev_sample || n <= 0) return MI3D_ERR_ARG;
+    sd::k_ddim_step<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(noise_pred, latents_noisy, alphas_cumprod, t, prev_sample, n);
+    return (int)cudaGetLastError();
+}
+
+// nerf/sd.py:201-210 decode_latents: imgs = (vae.decode(latents / 0.18215).sample / 2 + 0.5).clamp(0, 1); latents fp32 [1,4,h,w] -> imgs fp32 [1,3,S,S]
+int mi3d_sd_decode(mi3d_sd_t h, const float* latents, float* imgs, mi3d_stream_t stream) {
+    if (!h || h->e.vcfg.n_levels == 0 || !h->e.vcfg.decoder || !latents || !imgs) return MI3D_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream; sd::Engine& e = h->e;
+    const int pix = (int)e.dec_in.rows(), S = e.vcfg.image_hw;
+    const float* qw = (const float*)e.params[e.pindex["post_quant_conv.weight"]].dst; const float* qb = (const float*)e.params[e.pindex["post_quant_conv.bias"]].dst;
+    sd::k_dec_in<<<(pix + 127) / 128, 128, 0, st>>>(latents, qw, qb, e.dec_in.p, pix);
+    int r = e.run(e.dec_ops, st); if (r) return r;
+    sd::k_dec_out<<<(S * S + 127) / 128, 128, 0, st>>>(e.dec_out, imgs, S * S);
     return (int)cudaGetLastError();
 }
 

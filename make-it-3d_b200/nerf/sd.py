@@ -9,9 +9,9 @@ call and no CPU fallback.
 Weights: parameters are enumerated by diffusers' state_dict names; real SD-2.0-base checkpoints load through
 `load_diffusers_state_dict(unet_state, vae_state)` (which also pushes them into the engine); offline (no network, no weights on disk) they are seeded random tensors with PyTorch's default
 initialisers -- which is what the benchmark and the parity tests use (`data: synthetic`).
-What is NOT built ("next"): the text encoder, VAE decoder and the CLIP "denoise" side branch
-(nerf/sd.py:153-159).  That branch yields no gradient to any optimised parameter; here it returns (0, None) without
-running, which leaves the optimisation trajectory identical.
+The "denoise" side branch (nerf/sd.py:153-159: DDIM step t -> t-1, VAE decode, CLIP losses) is built on the same engine (`mi3d_sd_ddim_step`,
+`mi3d_sd_decode`); the CLIP losses run on a caller-provided clip_model (the reference passes it in too) and are skipped without one.
+What is NOT built: the CLIP text encoder behind `get_text_embeds` (deterministic stand-in) and CLIP itself.
 """
 import contextlib
 import ctypes as C
@@ -33,7 +33,7 @@ class UNetCfg(C.Structure):
 
 class VaeCfg(C.Structure):
     _fields_ = [("in_ch", C.c_int), ("latent_ch", C.c_int), ("n_levels", C.c_int), ("block_out", C.c_int * 4), ("layers_per_block", C.c_int),
-                ("groups", C.c_int), ("image_hw", C.c_int)]
+                ("groups", C.c_int), ("image_hw", C.c_int), ("decoder", C.c_int)]
 
 
 def sd20_unet_cfg(latent_hw=64):
@@ -63,6 +63,7 @@ def _vae_struct(cfg):
     for i, c in enumerate(cfg["block_out"]):
         v.block_out[i] = c
     v.layers_per_block, v.groups, v.image_hw = cfg["layers_per_block"], cfg["groups"], cfg["image_hw"]
+    v.decoder = 1 if cfg.get("decoder", True) else 0
     return v
 
 
@@ -225,9 +226,10 @@ class StableDiffusion(nn.Module):
         for name, shape in zip(self.engine.names, self.engine.shapes):
             if "#" in name:
                 continue
-            is_vae = name.startswith("encoder.") or name.startswith("quant_conv.")
+            is_vae = name.split(".")[0] in ("encoder", "quant_conv", "decoder", "post_quant_conv")
             src = (vae_state if is_vae else unet_state)
-            t = src[name].detach().float() if src is not None else _default_init(name, shape, gen)
+            # tensors absent from a given state (e.g. an encoder-only VAE state) keep the seeded default initialisation
+            t = src[name].detach().float() if (src is not None and name in src) else _default_init(name, shape, gen)
             p = nn.Parameter(t.to(self.device).contiguous(), requires_grad=False)
             (self.vae if is_vae else self.unet)[name.replace(".", "/")] = p
             tensors[name] = p.data
@@ -272,6 +274,52 @@ class StableDiffusion(nn.Module):
             eps = torch.randn(1, 4, hw, hw, device=self.device)
         return _EncodeImgs.apply(imgs, L.f32c(eps), self.engine)
 
+    def decode_latents(self, latents):
+        """nerf/sd.py:201-210: (vae.decode(latents / 0.18215).sample / 2 + 0.5).clamp(0, 1) -> [1,3,S,S]; no gradient, like the reference"""
+        latents = L.f32c(latents.detach())
+        S = self.vae_cfg["image_hw"]
+        imgs = torch.empty(1, 3, S, S, dtype=torch.float32, device=latents.device)
+        with self.engine.on_stream():
+            L.check(L.lib().mi3d_sd_decode(self.engine.h, L.ptr(latents), L.ptr(imgs), L.stream()), "sd_decode")
+        return imgs
+
+    def ddim_prev_sample(self, noise_pred, latents_noisy, t_dev):
+        """scheduler.set_timesteps(1000); scheduler.step(noise_pred, t, latents_noisy)['prev_sample'] (nerf/sd.py:154-155)"""
+        noise_pred, latents_noisy = L.f32c(noise_pred), L.f32c(latents_noisy)
+        out = torch.empty_like(latents_noisy)
+        L.check(L.lib().mi3d_sd_ddim_step(L.ptr(noise_pred), L.ptr(latents_noisy), L.ptr(t_dev), L.ptr(self.alphas), L.ptr(out),
+                                          C.c_int(out.numel()), L.stream()), "sd_ddim_step")
+        return out
+
+    @staticmethod
+    def img_clip_loss(clip_model, rgb1, rgb2, aug=None):
+        """nerf/sd.py:97-104 on a caller-provided CLIP model (openai `clip` is outside the hot path and not shipped here)"""
+        aug = aug or (lambda x: x)
+        z1, z2 = clip_model.encode_image(aug(rgb1)), clip_model.encode_image(aug(rgb2))
+        z1, z2 = z1 / z1.norm(dim=-1, keepdim=True), z2 / z2.norm(dim=-1, keepdim=True)
+        return -(z1 * z2).sum(-1).mean()
+
+    @staticmethod
+    def img_text_clip_loss(clip_model, rgb, text_tokens, aug=None):
+        """nerf/sd.py:106-114; `text_tokens` = clip.tokenize(prompt) done by the caller (the tokenizer belongs to the clip package)"""
+        aug = aug or (lambda x: x)
+        z1 = clip_model.encode_image(aug(rgb))
+        z1 = z1 / z1.norm(dim=-1, keepdim=True)
+        zt = clip_model.encode_text(text_tokens)
+        zt = zt / zt.norm(dim=-1, keepdim=True)
+        return -(z1 * zt).sum(-1).mean()
+
+    def _denoise_branch(self, noise_pred, latents_noisy, ref_rgb, ref_text, clip_model):
+        """nerf/sd.py:153-159: one DDIM step, decode, CLIP losses.  Nothing here carries a gradient to the NeRF (imgs comes out of
+        no_grad code in the reference too); without a clip_model the images are still produced (Trainer dumps them, utils.py:569)."""
+        de_latents = self.ddim_prev_sample(noise_pred, latents_noisy, self._t)
+        imgs = self.decode_latents(de_latents)
+        loss = 0
+        if clip_model is not None:
+            aug = getattr(self, "aug", None)
+            loss = 10 * self.img_clip_loss(clip_model, imgs, ref_rgb, aug) + 10 * self.img_text_clip_loss(clip_model, imgs, ref_text, aug)
+        return loss, imgs
+
     def unet_sds(self, latents, noise, t, text_embeddings, guidance_scale):
         """add_noise -> U-Net -> CFG -> SDS gradient (nerf/sd.py:138-170). t: device int64 [1]. Returns (noise_pred, grad)."""
         latents, noise, text_embeddings = L.f32c(latents.detach()), L.f32c(noise), L.f32c(text_embeddings)
@@ -293,9 +341,7 @@ class StableDiffusion(nn.Module):
         else:
             t_host = int(t)
         self._t.fill_(t_host)
-        if self.defer_backward:
-            if not islarge and (t_host / self.num_train_timesteps) <= 0.4:
-                return 0, None
+        if self.defer_backward and not (not islarge and (t_host / self.num_train_timesteps) <= 0.4):
             with torch.no_grad():
                 hw = self.vae_cfg["image_hw"] // 8
                 eps = L.f32c(eps_posterior) if eps_posterior is not None else torch.randn(1, 4, hw, hw, device=self.device)
@@ -316,11 +362,15 @@ class StableDiffusion(nn.Module):
         latents = self.encode_imgs(pred_rgb, eps_posterior)
         if noise is None:
             noise = torch.randn_like(latents)
-        if not islarge and (t_host / self.num_train_timesteps) <= 0.4:
-            # CLIP "denoise" side branch (nerf/sd.py:153-159): no gradient path to the NeRF; not built
-            return 0, None
         with torch.no_grad():
             noise_pred, grad = self.unet_sds(latents, noise, self._t, text_embeddings, guidance_scale)
+            if not islarge and (t_host / self.num_train_timesteps) <= 0.4:
+                # the "denoise" side branch (nerf/sd.py:153-159): no SDS backward on this step, exactly like the reference
+                a = self.alphas[t_host]
+                latents_noisy = a.sqrt() * latents.detach() + (1 - a).sqrt() * noise            # scheduler.add_noise (nerf/sd.py:141)
+                if not self.vae_cfg.get("decoder", True):
+                    return 0, None
+                return self._denoise_branch(noise_pred, latents_noisy, ref_rgb, ref_text, clip_model)
         latents.backward(gradient=grad, retain_graph=True)
         self.last = dict(latents=latents.detach(), noise_pred=noise_pred, grad=grad, t=t_host)
         return loss, imgs

@@ -349,3 +349,76 @@ def _sds_core(unet, vae, text_embeddings, img, t, eps_posterior, eps_noise, guid
     if latents.requires_grad:
         latents.backward(gradient=grad, retain_graph=True)                # sd.py:171
     return dict(latents=latents.detach(), latents_noisy=latents_noisy, noise_pred=noise_pred, grad=grad)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The "denoise" side branch of train_step (nerf/sd.py:153-159): one DDIM step t -> t-1 and the VAE decoder (nerf/sd.py:201-210).
+# ------------------------------------------------------------------------------------------------------------
+class Decoder(nn.Module):
+    """diffusers `Decoder` of AutoencoderKL: conv_in, mid (res, attention, res), UpDecoderBlock2D x len(block_out) with
+    layers_per_block + 1 resnets each and nearest-2x + conv upsamplers on all but the last, GroupNorm + SiLU + conv_out."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        bo, L, g = cfg["block_out"], cfg["layers_per_block"], cfg["groups"]
+        rev = list(reversed(bo))
+        ch = rev[0]
+        self.conv_in = nn.Conv2d(cfg["latent_channels"], ch, 3, padding=1)
+        self.mid_block = _Block()
+        self.mid_block.resnets.append(ResnetBlock2D(ch, ch, 0, g, 1e-6))
+        self.mid_block.attentions.append(VaeAttention(ch, g))
+        self.mid_block.resnets.append(ResnetBlock2D(ch, ch, 0, g, 1e-6))
+        self.up_blocks = nn.ModuleList()
+        for i, co in enumerate(rev):
+            blk = _Block()
+            for j in range(L + 1):
+                blk.resnets.append(ResnetBlock2D(ch, co, 0, g, 1e-6))
+                ch = co
+            if i < len(rev) - 1:
+                blk.upsamplers = nn.ModuleList([Upsample2D(ch)])
+            self.up_blocks.append(blk)
+        self.conv_norm_out = nn.GroupNorm(g, ch, eps=1e-6)
+        self.conv_out = nn.Conv2d(ch, cfg["in_channels"], 3, padding=1)
+
+    def forward(self, z):
+        h = self.conv_in(z)
+        h = self.mid_block.resnets[0](h)
+        h = self.mid_block.attentions[0](h)
+        h = self.mid_block.resnets[1](h)
+        for blk in self.up_blocks:
+            for res in blk.resnets:
+                h = res(h)
+            if hasattr(blk, "upsamplers"):
+                h = blk.upsamplers[0](h)
+        return self.conv_out(F.silu(self.conv_norm_out(h)))
+
+
+class AutoencoderKLDecoder(nn.Module):
+    """`vae.decode(z).sample`: post_quant_conv (1x1) + decoder; parameter names as in AutoencoderKL.state_dict()."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.post_quant_conv = nn.Conv2d(cfg["latent_channels"], cfg["latent_channels"], 1)
+        self.decoder = Decoder(cfg)
+
+    def forward(self, z):
+        return self.decoder(self.post_quant_conv(z))
+
+
+def ddim_step_ref(noise_pred, t, latents_noisy, alphas=None):
+    """DDIMScheduler.step(model_output, t, sample) with eta = 0 after set_timesteps(num_train_timesteps) (nerf/sd.py:154-155):
+    prev = t - 1; alpha_prev = alphas_cumprod[prev] if prev >= 0 else alphas_cumprod[0] (set_alpha_to_one=False in SD's scheduler
+    config); epsilon prediction, no clipping: x0 = (x_t - sqrt(1 - a_t) eps) / sqrt(a_t); x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps."""
+    if alphas is None:
+        alphas = alphas_cumprod()
+    a_t = alphas[t]
+    a_prev = alphas[t - 1] if t - 1 >= 0 else alphas[0]
+    x0 = (latents_noisy - (1 - a_t).sqrt() * noise_pred) / a_t.sqrt()
+    return a_prev.sqrt() * x0 + (1 - a_prev).sqrt() * noise_pred
+
+
+def decode_latents_ref(vae_dec, latents):
+    """nerf/sd.py:201-210"""
+    with torch.no_grad():
+        imgs = vae_dec(latents / 0.18215)
+    return (imgs / 2 + 0.5).clamp(0, 1)

@@ -156,6 +156,10 @@ def test_sd_oracle_two_independent_restatements_agree():
         big_v = sd_ref.AutoencoderKLEncoder(sd_ref.sd_vae_config())
     assert sum(p.numel() for p in big_u.parameters()) == 865910724
     assert sum(p.numel() for p in big_v.parameters()) == 34163592 + 72          # encoder 34 163 592 + quant_conv 8*8+8
+    with torch.device("meta"):
+        big_d = sd_ref.AutoencoderKLDecoder(sd_ref.sd_vae_config())
+    # the whole SD AutoencoderKL is published with 83 653 863 parameters: encoder + quant_conv + post_quant_conv + decoder
+    assert sum(p.numel() for p in big_v.parameters()) + sum(p.numel() for p in big_d.parameters()) == 83653863
     # the scheduler constants: SD scheduler_config.json (scaled_linear 0.00085 .. 0.012, 1000 steps), known end points
     ac = sd_ref.alphas_cumprod()
     assert abs(float(ac[0]) - 0.99915) < 1e-6 and abs(float(ac[999]) - 0.0046602) < 1e-6

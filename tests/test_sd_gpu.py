@@ -105,9 +105,11 @@ def test_train_step_drop_in_semantics(tiny):
     e, c = _rel(rgb.grad, rgb_ref.grad)
     print(f"SDS d pred_rgb rel_l2={e:.3e} cos={c:.6f}")
     assert e < 5e-2 and c > 0.998
+    # small t on a non-large view: the "denoise" side branch (sd.py:153-159) -- DDIM step + VAE decode, NO SDS backward that step
     rgb2 = rgb.detach().clone().requires_grad_()
     loss, imgs = g.train_step(ctx, rgb2, islarge=False, t=300)
-    assert loss == 0 and imgs is None and rgb2.grad is None
+    assert loss == 0 and rgb2.grad is None                      # no clip_model passed: images only
+    assert imgs.shape == (1, 3, 256, 256) and float(imgs.min()) >= 0.0 and float(imgs.max()) <= 1.0 and torch.isfinite(imgs).all()
 
 
 def test_graph_replay_is_bit_identical_to_plain_launches(tiny):
@@ -161,8 +163,45 @@ def test_deferred_sds_backward_gives_the_same_gradient(tiny):
         assert imgs is None and torch.is_tensor(loss) and b.grad is None
         (loss + 0.0).backward()
         z = rgb.clone().requires_grad_()
-        l0, _ = g.train_step(ctx, z, islarge=False, t=300)
-        assert l0 == 0 and z.grad is None
+        l0, im0 = g.train_step(ctx, z, islarge=False, t=300)
+        assert l0 == 0 and z.grad is None and im0 is not None
     finally:
         g.defer_backward = False
     assert float((a.grad - b.grad).abs().max()) <= 1e-5 * float(a.grad.abs().max())
+
+
+def test_denoise_branch_matches_oracle(tiny):
+    """DDIM step t -> t-1 (DDIMScheduler.step, eta 0) and decode_latents (AutoencoderKL.decode, nerf/sd.py:201-210) vs the fp32 oracle;
+    the CLIP losses of the branch run on whatever clip_model the caller passes (a stand-in with encode_image / encode_text here)."""
+    sdm, g, unet, vae = tiny
+    dec = sd_ref.AutoencoderKLDecoder(sd_ref.tiny_vae_config()).eval()
+    with torch.no_grad():
+        for m in dec.modules():
+            if isinstance(m, torch.nn.GroupNorm):
+                m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.3, 0.3)
+    g.load_diffusers_state_dict(vae_state={**vae.state_dict(), **dec.state_dict()})
+    gen = torch.Generator().manual_seed(21)
+    npred, xt = torch.randn(1, 4, 32, 32, generator=gen), torch.randn(1, 4, 32, 32, generator=gen)
+    for t in (0, 1, 399):
+        ref = sd_ref.ddim_step_ref(npred, t, xt)
+        got = g.ddim_prev_sample(npred.cuda(), xt.cuda(), torch.tensor([t], dtype=torch.long, device="cuda"))
+        assert float((got.cpu() - ref).abs().max()) <= 2e-6 * float(ref.abs().max()), t
+    lat = torch.randn(1, 4, 32, 32, generator=gen) * 0.18215 * 1.5
+    ref = sd_ref.decode_latents_ref(dec, lat)
+    got = g.decode_latents(lat.cuda())
+    torch.cuda.synchronize()
+    e, c = _rel(got, ref)
+    print(f"decode_latents rel_l2={e:.3e} cos={c:.6f}")
+    assert got.shape == (1, 3, 256, 256) and e < 1e-2 and c > 0.9999
+
+    class FakeClip:
+        def encode_image(self, x):
+            return x.mean(dim=(2, 3)) @ torch.ones(3, 8, device=x.device)
+
+        def encode_text(self, tok):
+            return tok.float()
+    rgb = torch.rand(1, 3, 64, 64, generator=gen).cuda().requires_grad_()
+    ctx = torch.randn(2, 77, 128, generator=gen).cuda()
+    loss, imgs = g.train_step(ctx, rgb, islarge=False, t=350, ref_rgb=torch.rand(1, 3, 256, 256, device="cuda"),
+                              ref_text=torch.ones(1, 8, device="cuda"), clip_model=FakeClip())
+    assert torch.is_tensor(loss) and torch.isfinite(loss) and imgs.shape == (1, 3, 256, 256) and rgb.grad is None
