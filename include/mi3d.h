@@ -152,8 +152,11 @@ typedef struct { float *w1, *b1, *w2, *b2, *w3, *b3; } mi3d_mlp_grad;
 enum { MI3D_SHADING_ALBEDO = 0, MI3D_SHADING_LAMBERTIAN = 1, MI3D_SHADING_TEXTURELESS = 2, MI3D_SHADING_NORMAL = 3 };
 /* kernel family of the fused field.  TCGEN05 (default): tcgen05 split-precision tiles; the backward chain kernel issues the
  * table-gradient REDs itself (LSU-bound RED stream under the latency-bound MMA chain; = _FUSED_SCATTER).  _SPLIT_SCATTER: the
- * round-1 pipeline with a separate full-occupancy scatter kernel (A/B arm).  FFMA = the register-tiled fp32 kernels. */
-enum { MI3D_FIELD_IMPL_TCGEN05 = 0, MI3D_FIELD_IMPL_FFMA = 1, MI3D_FIELD_IMPL_TCGEN05_FUSED_SCATTER = 2, MI3D_FIELD_IMPL_TCGEN05_SPLIT_SCATTER = 3 };
+ * round-1 pipeline with a separate full-occupancy scatter kernel (A/B arm).  _SINGLE_E: fused scatter, but the encoding operand of the
+ * chain kernel single-buffered (the default alternates consecutive evaluations between the two column halves of its tile; A/B arm).
+ * FFMA = the register-tiled fp32 kernels. */
+enum { MI3D_FIELD_IMPL_TCGEN05 = 0, MI3D_FIELD_IMPL_FFMA = 1, MI3D_FIELD_IMPL_TCGEN05_FUSED_SCATTER = 2, MI3D_FIELD_IMPL_TCGEN05_SPLIT_SCATTER = 3,
+       MI3D_FIELD_IMPL_TCGEN05_SINGLE_E = 4 };
 
 typedef struct {
     float bound;          /* opt.bound */
@@ -165,6 +168,7 @@ typedef struct {
     float ambient_ratio;
     const float* light_d; /* device [3] (multi-view batches: [n_views][3]), needed unless shading == albedo */
     int impl;             /* MI3D_FIELD_IMPL_* (explicit: the library reads no environment variables) */
+    float scatter_agg_scale; /* tuning knob of the fused scatter: REDs of hash-grid levels with scale below this are warp-aggregated; 0 = library default (50) */
 } mi3d_field_cfg;
 
 /* Multi-view batches (several camera views' rays in one march: ray-parallel multi-GPU render, or several views per GPU).

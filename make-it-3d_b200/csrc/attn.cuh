@@ -60,7 +60,7 @@ static __global__ void __launch_bounds__(kThreads, 2)
 k_flash_attn(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
              const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS / LDS, not generic ST / LD)
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + kTile;            // two stages
     uint8_t* sV = sK + 2 * kTile;
@@ -96,34 +96,47 @@ k_flash_attn(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 
     if (warp == 4) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // whole warp on the (uniform) loop and the barrier waits, one elected lane issues: see tc::elect_one()
+        if (elect_one()) {
             mbar_arrive_expect_tx(q_full, kTile);
             tma_load_4d(&map_q, q_full, sQ, 0, q0, head, batch);
-            for (int j = 0; j < nkv; j++) {
-                const int st = j & 1;
-                mbar_wait(&k_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        for (int j = 0; j < nkv; j++) {
+            const int st = j & 1;
+            mbar_wait(&k_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&k_full[st], kTile);
                 tma_load_4d(&map_k, &k_full[st], sK + st * kTile, 0, j * 128, head, batch);
-                mbar_wait(v_empty, ((uint32_t)j & 1u) ^ 1u);
+            }
+            __syncwarp();
+            mbar_wait(v_empty, ((uint32_t)j & 1u) ^ 1u);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(v_full, kTile);
                 tma_load_4d(&map_v, v_full, sV, 0, j * 128, head, batch);
             }
+            __syncwarp();
         }
     } else if (warp == 5) {
         // ===================== tcgen05 issuer =====================
-        if (lane == 0) {
+        // whole warp on the (uniform) loop and the barrier waits, one elected lane issues: see tc::elect_one()
+        {
             const uint32_t idesc_s = make_idesc_f16(128, 128, 0), idesc_pv = make_idesc_f16(128, 64, 1);
-            const uint64_t dq = make_sw128_desc(smem_u32(sQ));
-            const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t sq_u = __shfl_sync(0xffffffffu, smem_u32(sQ), 0), sk_u = sq_u + (uint32_t)kTile, sv_u = sk_u + 2u * (uint32_t)kTile, sp_u = sv_u + (uint32_t)kTile;
+            const uint32_t tmem_s = tmem_u, tmem_pv = tmem_u + 128;
             auto issue_s = [&](int j) {
                 const int st = j & 1;
                 mbar_wait(&k_full[st], ((uint32_t)j >> 1) & 1u);
                 tc_fence_after();
-                const uint64_t dk = make_sw128_desc(smem_u32(sK + st * kTile));
-                #pragma unroll
-                for (int k = 0; k < 4; k++) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(s_full);
-                umma_commit(&k_empty[st]);
+                if (elect_one()) {
+                    const uint64_t dq = make_sw128_desc(sq_u), dk = make_sw128_desc(sk_u + (uint32_t)(st * kTile));
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) umma_f16(tmem_s, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit(s_full);
+                    umma_commit(&k_empty[st]);
+                }
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             issue_s(0);
@@ -131,15 +144,18 @@ k_flash_attn(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 mbar_wait(p_full, (uint32_t)j & 1u);              // S(j) drained from TMEM, P(j) in shared memory, O row rescaled if needed
                 mbar_wait(v_full, (uint32_t)j & 1u);
                 tc_fence_after();
-                const uint64_t dv = make_sw128_desc_mn(smem_u32(sV), 8192u);
-                #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint64_t dp = make_sw128_desc(smem_u32(sP + (k >> 2) * kTile)) + (uint64_t)(2 * (k & 3));
-                    umma_f16(tmem_pv, dp, dv + (uint64_t)(128 * k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                if (elect_one()) {
+                    const uint64_t dv = make_sw128_desc_mn(sv_u, 8192u);
+                    #pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint64_t dp = make_sw128_desc(sp_u + (uint32_t)((k >> 2) * kTile)) + (uint64_t)(2 * (k & 3));
+                        umma_f16(tmem_pv, dp, dv + (uint64_t)(128 * k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(v_empty);
+                    if (j + 1 >= nkv) umma_commit(pv_full);       // O complete
                 }
-                umma_commit(v_empty);
+                __syncwarp();
                 if (j + 1 < nkv) issue_s(j + 1);                  // in-order pipe: s_full(j+1) also certifies that MMA2(j) has retired
-                else umma_commit(pv_full);                        // O complete
             }
         }
     } else {

@@ -169,13 +169,17 @@ __device__ __forceinline__ void scatter_level_agg(float* __restrict__ gtable, co
     }
 }
 
+// The chain kernel's gather / scatter threads own (row, half) with the 16 levels dealt out in PAIRS: half h holds levels
+// {4j + 2h, 4j + 2h + 1 : j = 0..3}, i.e. encoding columns [8j + 4h, 8j + 4h + 4).  (A contiguous split gave every warp-aggregated
+// coarse level to half 0 and made those four warps the slowest link of the fused scatter.)
+__device__ __forceinline__ int half_level(int i, int half) { return ((i >> 1) << 2) + 2 * half + (i & 1); }
+
 // single-level-at-a-time variant (8 loads in flight): lower register pressure, used by the backward's prefetch
-__device__ __forceinline__ void gather16s(const float* __restrict__ table, const LevelSm* __restrict__ lv, int l0, int lcount,
+__device__ __forceinline__ void gather16s(const float* __restrict__ table, const LevelSm* __restrict__ lv, int half,
                                           float u0, float u1, float u2, float (&f)[16]) {
     #pragma unroll
     for (int i = 0; i < 8; i++) {
-        if (i >= lcount) { f[2 * i] = 0.f; f[2 * i + 1] = 0.f; continue; }
-        const LevelSm L = lv[l0 + i];
+        const LevelSm L = lv[half_level(i, half)];
         const CellW cw = hg_cell(u0, u1, u2, L.scale);
         const float2* __restrict__ base = reinterpret_cast<const float2*>(table) + L.offset;
         float2 v[8];
@@ -645,6 +649,7 @@ constexpr size_t kSmem = 1024 + oMisc + 2048;
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int kblocks,
                                             uint32_t a_kb_stride, uint32_t b_kb_stride, uint32_t idesc) {
     uint32_t acc = 0;
+    #pragma unroll
     for (int kb = 0; kb < kblocks; kb++) {
         const uint64_t dah = tc::make_sw128_desc(a_hi + kb * a_kb_stride), dal = tc::make_sw128_desc(a_lo + kb * a_kb_stride);
         const uint64_t dbh = tc::make_sw128_desc(b_hi + kb * b_kb_stride), dbl = tc::make_sw128_desc(b_lo + kb * b_kb_stride);
@@ -662,7 +667,7 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint
 __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdArgs a) {
     using namespace fwdtc;
     extern __shared__ uint8_t smem_dyn[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sm = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS / LDS, not generic ST / LD)
     float* b1s = reinterpret_cast<float*>(sm + oMisc);          // 64
     float* b2s = b1s + 64;                                      // 64
     float* b3s = b2s + 64;                                      // 4 (+pad)
@@ -890,24 +895,37 @@ __global__ void __launch_bounds__(fwdtc::kThreads, 1) k_field_fwd_tc(const FwdAr
         }
     } else {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // whole warp on the (uniform) loop and the barrier waits, one elected lane issues: see tc::elect_one()
+        {
             constexpr uint32_t id64 = idesc_tf32(128, 64), id16 = idesc_tf32(128, 16);
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0), sb0 = __shfl_sync(0xffffffffu, sbase, 0);
             for (uint32_t tile = blockIdx.x; (uint64_t)tile * T < m_pad; tile += gridDim.x) {
                 for (int e = 0; e < n_evals; e++, it++) {
+                    uint32_t sb = sb0;
+                    asm volatile("" : "+r"(sb));            // keeps the (loop-invariant) descriptors from being hoisted and spilled
                     const uint32_t par = it & 1;
                     tc::mbar_wait(a1_full, par);
                     tc::tc_fence_after();
-                    issue_layer(tmem, sbase + oA1H, sbase + oA1L, sbase + oW1H, sbase + oW1L, 1, kA1, 8192, id64);
-                    tc::umma_commit(a1_empty);
-                    tc::umma_commit(d1_full);
+                    if (tc::elect_one()) {
+                        issue_layer(tm, sb + oA1H, sb + oA1L, sb + oW1H, sb + oW1L, 1, kA1, 8192, id64);
+                        tc::umma_commit(a1_empty);
+                        tc::umma_commit(d1_full);
+                    }
+                    __syncwarp();
                     tc::mbar_wait(a2_full, par);
                     tc::tc_fence_after();
-                    issue_layer(tmem + 64u, sbase + oA2H, sbase + oA2L, sbase + oW2H, sbase + oW2L, 2, kA1, 8192, id64);
-                    tc::umma_commit(d2_full);
+                    if (tc::elect_one()) {
+                        issue_layer(tm + 64u, sb + oA2H, sb + oA2L, sb + oW2H, sb + oW2L, 2, kA1, 8192, id64);
+                        tc::umma_commit(d2_full);
+                    }
+                    __syncwarp();
                     tc::mbar_wait(a3_full, par);
                     tc::tc_fence_after();
-                    issue_layer(tmem + 128u, sbase + oA2H, sbase + oA2L, sbase + oW3H, sbase + oW3L, 2, kA1, 2048, id16);
-                    tc::umma_commit(d3_full);
+                    if (tc::elect_one()) {
+                        issue_layer(tm + 128u, sb + oA2H, sb + oA2L, sb + oW3H, sb + oW3L, 2, kA1, 2048, id16);
+                        tc::umma_commit(d3_full);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -967,6 +985,7 @@ struct BwdArgs {
     float* enc_buf; float* denc_buf; uint32_t tile0, tile1;
     const mi3d_view_segs* segs; uint32_t noise_mode;   // multi-view: g_loss_orient / g_loss_smooth are [n_views] arrays
     float agg_scale_max;                               // fused scatter: warp-aggregate the REDs of levels with scale below this
+    int e_pingpong;                                    // chain kernel: encodings of consecutive evaluations alternate between the two column halves of the E tile
 };
 
 // d(loss)/d(h) of the 13 evaluations of one sample from the upstream gradients and the forward tape (sigma0, albedo, tap sigmas):
@@ -1148,10 +1167,11 @@ __global__ void __launch_bounds__(NT, 1) k_field_bwd(const BwdArgs a) {
     }
 }
 
+// the 16 encoding columns of one (row, half): four 16-byte chunks, 8 floats apart (see half_level)
 __device__ __forceinline__ void load16(const float* __restrict__ src, float (&f)[16]) {
     #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + 2 * q);
         f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
     }
 }
@@ -1290,7 +1310,7 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
     }
     __shared__ mi3d_view_segs segs_sm;
     extern __shared__ uint8_t smem_dyn[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sm = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS / LDS, not generic ST / LD)
     float* b1s = reinterpret_cast<float*>(sm + oMisc);          // 64
     float* b2s = b1s + 64;                                      // 64
     float* w3s = b2s + 64;                                      // [4][64]
@@ -1494,9 +1514,8 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
     } else if (warp < 12) {
         // ================================ encoders / scatterers ================================
         const int et = tid - 128, r = et & (T - 1), half = et >> 7;
-        const int nl = (int)a.hg.n_levels, l0 = half * (nl / 2), lcount = half ? nl - nl / 2 : nl / 2;
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const bool ext = a.enc_buf != nullptr, ext_out = a.denc_buf != nullptr;
+        const bool ext = a.enc_buf != nullptr, ext_out = a.denc_buf != nullptr, pp = a.e_pingpong != 0;
         for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
             const uint32_t row = tile * T + r;
             const RowInfo ri = row_info(R, row);
@@ -1509,95 +1528,129 @@ __global__ void __launch_bounds__(bwdtc::kThreads, 1) k_field_bwd_tc(const BwdAr
                 #pragma unroll
                 for (int c = 0; c < 3; c++) xp[c] = x[c] + z[c] * kSmoothStd;
             }
-            // Software pipeline over the evaluations of this tile:
-            //   write E(e+1) as soon as chain(e) has retired (d4) and BEFORE scattering dEnc(e), so that the MMA / epilogue chain of
-            //   e+1 overlaps the scatter of e and the gather of e+2.
+            // Software pipeline over the evaluations of this tile.
+            //   single-buffered E (pp == false): write E(e+1) as soon as chain(e) has retired (d4) and BEFORE scattering dEnc(e), so that the
+            //     MMA / epilogue chain of e+1 overlaps the scatter of e and the gather of e+2.  The hand-off (d4 -> TMEM load -> split -> store ->
+            //     a1) sits on the chain's critical path.
+            //   ping-pong E (pp == true): the encoding uses 32 of the tile's 64 columns, so evaluation `it` lives in columns 32 (it & 1) .. + 31
+            //     (operand start address + 64 B).  E(it+2) is written at the END of iteration `it` (its half was last read by chain(it), retired
+            //     at d4(it)); chain(it+1) then starts the moment chain(it) retires -- the MMA warp has already seen a1(it+1).
             float f[16];
-            auto write_E = [&](const float (&ff)[16]) {
+            auto write_E = [&](const float (&ff)[16], const uint32_t itw) {
+                const int ecol = pp ? 32 * (int)(itw & 1u) : 0;
                 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    if (i >= lcount) continue;
-                    const int k = 2 * (l0 + i);
-                    __nv_bfloat16 h0, m0, q0, h1, m1b, q1;
-                    split3(ff[2 * i], h0, m0, q0); split3(ff[2 * i + 1], h1, m1b, q1);
+                    const int k = 2 * half_level(i, half) + ecol;
+                    uint32_t h2, m2, l2;
+                    split3x2(ff[2 * i], ff[2 * i + 1], h2, m2, l2);
                     const uint32_t o = oE + sw_off16(r, k);
-                    *reinterpret_cast<__nv_bfloat162*>(sm + o) = __halves2bfloat162(h0, h1);
-                    *reinterpret_cast<__nv_bfloat162*>(sm + o + kTile) = __halves2bfloat162(m0, m1b);
-                    *reinterpret_cast<__nv_bfloat162*>(sm + o + 2 * kTile) = __halves2bfloat162(q0, q1);
+                    *reinterpret_cast<uint32_t*>(sm + o) = h2;
+                    *reinterpret_cast<uint32_t*>(sm + o + kTile) = m2;
+                    *reinterpret_cast<uint32_t*>(sm + o + 2 * kTile) = l2;
                 }
                 tc::fence_proxy_async();
                 mbar_arrive(a1_full);
             };
-            {
+            auto fetch = [&](const int e, float (&ff)[16]) {
+                if (ext) { load16(a.enc_buf + ((size_t)(tile - a.tile0) * 13 + e) * (T * 32) + (size_t)r * 32 + 4 * half, ff); return; }
                 float p[3];
-                eval_pos(0, x, xp, a.bound, p);
-                if (ext) load16(a.enc_buf + ((size_t)(tile - a.tile0) * 13 + 0) * (T * 32) + (size_t)r * 32 + 16 * half, f);
-                else gather16s(a.table, lv, l0, lcount, (p[0] + a.bound) / inv2b, (p[1] + a.bound) / inv2b, (p[2] + a.bound) / inv2b, f);
-                write_E(f);            // E is free: this thread waited for d4 of the previous evaluation (or it is the first one)
+                eval_pos(e, x, xp, a.bound, p);
+                gather16s(a.table, lv, half, (p[0] + a.bound) / inv2b, (p[1] + a.bound) / inv2b, (p[2] + a.bound) / inv2b, ff);
+            };
+            fetch(0, f);
+            write_E(f, it);            // E (pp: this half) is free: this thread waited for d4 of the evaluations that read it
+            if (pp && e_end > 1) {
+                fetch(1, f);
+                // a1 may run at most one phase ahead of its waiter: F1(it) issued (d1) => the MMA warp has consumed a1 phase `it`
+                tc::mbar_wait(d1_full, it & 1);
+                write_E(f, it + 1);
             }
             for (int e = 0; e < e_end; e++, it++) {
                 const uint32_t par = it & 1;
                 float p[3];
                 eval_pos(e, x, xp, a.bound, p);
                 const float u0 = (p[0] + a.bound) / inv2b, u1 = (p[1] + a.bound) / inv2b, u2 = (p[2] + a.bound) / inv2b;
-                // prefetch the next evaluation's gather while the MMA / epilogue chain of this one runs
-                if (e + 1 < e_end) {
-                    float pn[3];
-                    eval_pos(e + 1, x, xp, a.bound, pn);
-                    if (ext) load16(a.enc_buf + ((size_t)(tile - a.tile0) * 13 + (e + 1)) * (T * 32) + (size_t)r * 32 + 16 * half, f);
-                    else gather16s(a.table, lv, l0, lcount, (pn[0] + a.bound) / inv2b, (pn[1] + a.bound) / inv2b, (pn[2] + a.bound) / inv2b, f);
-                }
+                const int en = pp ? e + 2 : e + 1;              // the evaluation whose encodings this iteration hands over
+                // single-buffered: prefetch the next evaluation's gather while the MMA / epilogue chain of this one runs
+                if (!pp && en < e_end) fetch(en, f);
                 // dEnc (this thread's 16 columns of its row) straight from TMEM into registers
                 tc::mbar_wait(d4_full, par);
                 tc::tc_fence_after();
                 uint32_t g[16];
-                tmem_ld16(lane_addr + cG1 + (uint32_t)(2 * l0), g);
+                tmem_ld4x4(lane_addr + cG1 + (uint32_t)(4 * half), g);      // columns 8j + 4 half .. + 3, j = 0..3
                 tc::tc_fence_before();
                 // chain(e) has retired: E is free -> hand the next evaluation to the MMA warp before scattering this one
-                if (e + 1 < e_end) write_E(f);
+                if (!pp && en < e_end) write_E(f, it + 1);
+                if (pp && en < e_end) fetch(en, f);            // ping-pong: loads in flight under the scatter
                 if (ext_out) {
-                    float4* dst = reinterpret_cast<float4*>(a.denc_buf + ((size_t)(tile - a.tile0) * 13 + e) * (T * 32) + (size_t)r * 32 + 16 * half);
+                    float4* dst = reinterpret_cast<float4*>(a.denc_buf + ((size_t)(tile - a.tile0) * 13 + e) * (T * 32) + (size_t)r * 32 + 4 * half);
                     #pragma unroll
-                    for (int q = 0; q < 4; q++) dst[q] = make_float4(__uint_as_float(g[4 * q]), __uint_as_float(g[4 * q + 1]), __uint_as_float(g[4 * q + 2]), __uint_as_float(g[4 * q + 3]));
+                    for (int q = 0; q < 4; q++) dst[2 * q] = make_float4(__uint_as_float(g[4 * q]), __uint_as_float(g[4 * q + 1]), __uint_as_float(g[4 * q + 2]), __uint_as_float(g[4 * q + 3]));
                 } else
                 #pragma unroll 1
-                for (int i = 0; i < lcount; i++) {
+                for (int i = 0; i < 8; i++) {
                     float g0 = 0.f, g1 = 0.f;
                     #pragma unroll
                     for (int q = 0; q < 8; q++) if (q == i) { g0 = __uint_as_float(g[2 * q]); g1 = __uint_as_float(g[2 * q + 1]); }
-                    const LevelSm L = lv[l0 + i];
+                    const LevelSm L = lv[half_level(i, half)];
                     // aggregate where a cell spans several march steps (2 / scale  >  ~1.5 dt_min): levels 0..7 of the reference grid
                     scatter_level_agg(a.g_table, L, u0, u1, u2, g0, g1, in_range, L.scale < a.agg_scale_max, lane);
                 }
+                if (pp && en < e_end) write_E(f, it + 2);
             }
         }
     } else {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
-            // MN-major with M = 128 reads a second 64-column block at +lbo: it lands on the next part tile (finite; rows 64.. of D unused)
-            const Operand Ek{sbase + oE, (uint32_t)kTile, 16u, 0}, Em{sbase + oE, (uint32_t)kTile, (uint32_t)kTile, 1};
-            const Operand Hk{sbase + oH, (uint32_t)kTile, 16u, 0}, Hm{sbase + oH, (uint32_t)kTile, (uint32_t)kTile, 1};
-            const Operand Zk{sbase + oZ, (uint32_t)kTile, 16u, 0}, Zm{sbase + oZ, (uint32_t)kTile, (uint32_t)kTile, 1};
-            const Operand W1k{sbase + oW1, 8192u, 16u, 0}, W1m{sbase + oW1, 8192u, 8192u, 1};
-            const Operand W2k{sbase + oW2, 8192u, 16u, 0}, W2m{sbase + oW2, 8192u, 8192u, 1};
+        // The whole warp walks the loop and the barrier waits; one elected lane issues.  tmem / smem bases go through a lane-0 broadcast so
+        // that the compiler keeps every tcgen05 operand in uniform registers (see tc::elect_one).
+        {
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0), sb0 = __shfl_sync(0xffffffffu, sbase, 0);
+            const bool pp = a.e_pingpong != 0;
             uint32_t accW = 0;
             for (uint32_t tile = a.tile0 + blockIdx.x; tile < a.tile1 && (uint64_t)tile * T < m_pad; tile += gridDim.x) {
                 for (int e = 0; e < e_end; e++, it++) {
+                    // the ~100 descriptors are loop-invariant; left alone the compiler hoists them all out of the loops and spills them.
+                    // Re-deriving them from an opaque copy of the base keeps them as a few uniform adds next to each use.
+                    uint32_t sb = sb0;
+                    asm volatile("" : "+r"(sb));
+                    // MN-major with M = 128 reads a second 64-column block at +lbo: it lands on the next part tile (finite; rows 64.. of D unused)
+                    const uint32_t eoff = pp ? 64u * (it & 1u) : 0u;            // ping-pong E: columns 32 (it & 1) .. + 31 of the tile
+                    const Operand Ek{sb + oE + eoff, (uint32_t)kTile, 16u, 0}, Em{sb + oE + eoff, (uint32_t)kTile, (uint32_t)kTile, 1};
+                    const Operand Hk{sb + oH, (uint32_t)kTile, 16u, 0}, Hm{sb + oH, (uint32_t)kTile, (uint32_t)kTile, 1};
+                    const Operand Zk{sb + oZ, (uint32_t)kTile, 16u, 0}, Zm{sb + oZ, (uint32_t)kTile, (uint32_t)kTile, 1};
+                    const Operand W1k{sb + oW1, 8192u, 16u, 0}, W1m{sb + oW1, 8192u, 8192u, 1};
+                    const Operand W2k{sb + oW2, 8192u, 16u, 0}, W2m{sb + oW2, 8192u, 8192u, 1};
                     const uint32_t par = it & 1;
-                    tc::mbar_wait(a1_full, par); tc::tc_fence_after();
-                    issue_bf16x3(tmem + cD1, Ek, W1k, 32, idesc_bf16(128, 64, 0, 0), 0);           // F1 (K = 32: the zero columns 32..63 of the tiles are skipped)
-                    tc::umma_commit(d1_full);
+                    if (!(pp && e > 0)) { tc::mbar_wait(a1_full, par); tc::tc_fence_after(); }     // ping-pong: consumed before d4 of the previous evaluation
+                    if (tc::elect_one()) {
+                        issue_bf16x3(tm + cD1, Ek, W1k, 32, idesc_bf16(128, 64, 0, 0), 0);           // F1 (K = 32: the zero columns 32..63 of the tiles are skipped)
+                        tc::umma_commit(d1_full);
+                    }
+                    __syncwarp();
                     tc::mbar_wait(a2_full, par); tc::tc_fence_after();
-                    issue_bf16x3(tmem + cD2, Hk, W2k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F2
-                    tc::umma_commit(d2_full);
+                    if (tc::elect_one()) {
+                        issue_bf16x3(tm + cD2, Hk, W2k, 64, idesc_bf16(128, 64, 0, 0), 0);           // F2
+                        tc::umma_commit(d2_full);
+                    }
+                    __syncwarp();
                     tc::mbar_wait(a3_full, par); tc::tc_fence_after();
-                    issue_bf16x3(tmem + cG2, Zk, W2m, 64, idesc_bf16(128, 64, 0, 1), 0);           // G2 : dH1 = dZ2 W2
-                    issue_bf16x3(tmem + cW2, Zm, Hm, 128, idesc_bf16(128, 64, 1, 1), accW);       // WG2: dW2 += dZ2^T H1
-                    tc::umma_commit(d3_full);
+                    if (tc::elect_one()) {
+                        issue_bf16x3(tm + cG2, Zk, W2m, 64, idesc_bf16(128, 64, 0, 1), 0);           // G2 : dH1 = dZ2 W2
+                        issue_bf16x3(tm + cW2, Zm, Hm, 128, idesc_bf16(128, 64, 1, 1), accW);       // WG2: dW2 += dZ2^T H1
+                        tc::umma_commit(d3_full);
+                    }
+                    __syncwarp();
                     tc::mbar_wait(a4_full, par); tc::tc_fence_after();
-                    issue_bf16x3(tmem + cG1, Zk, W1m, 64, idesc_bf16(128, 32, 0, 1), 0);           // G1 : dEnc = dZ1 W1
-                    issue_bf16x3(tmem + cW1, Zm, Em, 128, idesc_bf16(128, 32, 1, 1), accW);       // WG1: dW1 += dZ1^T Enc
-                    tc::umma_commit(d4_full);
+                    if (tc::elect_one()) {
+                        issue_bf16x3(tm + cG1, Zk, W1m, 64, idesc_bf16(128, 32, 0, 1), 0);           // G1 : dEnc = dZ1 W1
+                        issue_bf16x3(tm + cW1, Zm, Em, 128, idesc_bf16(128, 32, 1, 1), accW);       // WG1: dW1 += dZ1^T Enc
+                    }
+                    __syncwarp();
+                    // ping-pong: E(it+1) is already there (other half).  Consuming its a1 phase BEFORE releasing d4(it) keeps the encoders,
+                    // who arrive for it+2 only after d4(it), from lapping this waiter.
+                    if (pp && e + 1 < e_end) { tc::mbar_wait(a1_full, par ^ 1u); tc::tc_fence_after(); }
+                    if (tc::elect_one()) tc::umma_commit(d4_full);
+                    __syncwarp();
                     accW = 1;
                 }
             }
@@ -1842,6 +1895,7 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     a.g_loss_orient = grad_loss_orient; a.g_loss_smooth = grad_loss_smooth;
     a.g_table = grad_table; a.g_mlp = *grad_mlp;
     a.enc_buf = nullptr; a.denc_buf = nullptr; a.tile0 = 0; a.tile1 = 0xFFFFFFFFu; a.agg_scale_max = 50.f;
+    a.e_pingpong = cfg->impl != MI3D_FIELD_IMPL_TCGEN05_SINGLE_E && cfg->impl != MI3D_FIELD_IMPL_TCGEN05_SPLIT_SCATTER;
     a.segs = io->segs; a.noise_mode = io->noise_mode;
     if ((io->segs || io->noise_mode) && cfg->impl == MI3D_FIELD_IMPL_FFMA) return MI3D_ERR_ARG;
     if (io->segs && (io->n_views == 0 || io->n_views > MI3D_MAX_VIEWS)) return MI3D_ERR_ARG;
@@ -1864,7 +1918,7 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
                 // inside the chain kernel the 5-step shuffle scans of the warp aggregation compete with the owner warps for issue slots:
                 // aggregate only levels 0-3 (scale < 50, cells >= 7 march steps wide).  Measured (M = 424 k, full backward): threshold 200 ->
                 // 5.79 ms, 120 -> 5.56, 60 -> 5.29, 50 -> 5.36, 25 -> 6.74, no aggregation -> 11.7 (same-address RED serialisation in L2)
-                a.agg_scale_max = 50.f;
+                a.agg_scale_max = cfg->scatter_agg_scale > 0.f ? cfg->scatter_agg_scale : 50.f;
                 if (fuse) {
                     // the chain kernel's encoder warps scatter d(enc) themselves, straight from TMEM: the RED stream (LSU-bound) runs
                     // under the MMA / epilogue chain (latency-bound) of the next evaluation instead of in a kernel of its own

@@ -108,6 +108,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp (the lowest): callers keep the whole warp on the (warp-uniform) control path and predicate only the
+// tcgen05 issue on it -- with `if (lane == 0)` the compiler cannot prove that a single lane is active and wraps EVERY tcgen05.mma in a
+// uniform-register "waterfall" loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~12 SASS instructions and ~60 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
     using C = Cfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS / LDS, not generic ST / LD)
     uint8_t* tiles = smem;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)C::kStages * C::kStageBytes);
     uint64_t* empty_bar = full_bar + C::kStages;
@@ -204,7 +213,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // whole warp on the (uniform) loop and the barrier waits, one elected lane issues: see elect_one()
+        {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const int sp = t % p.splits, tt = t / p.splits;
@@ -223,51 +233,63 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = tiles + (size_t)stage * C::kStageBytes;
                     uint8_t* sb = sa + C::kABytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                    int c0 = kb * BLOCK_K, c1 = m0, c2 = az0, c3 = az1;
                     if (p.conv) {
                         const int tap = kb / p.cin_blocks, cc = kb - tap * p.cin_blocks;
                         const int ky = tap / 3, kx = tap - ky * 3;
-                        tma_load_4d(&map_a, &full_bar[stage], sa, cc * BLOCK_K, cw + kx - 1, ch + ky - 1, cn);
-                    } else {
-                        tma_load_4d(&map_a, &full_bar[stage], sa, kb * BLOCK_K, m0, az0, az1);
+                        c0 = cc * BLOCK_K; c1 = cw + kx - 1; c2 = ch + ky - 1; c3 = cn;
                     }
-                    if (p.b_mn) {
-                        #pragma unroll
-                        for (int nb = 0; nb < BLOCK_N / 64; nb++) tma_load_4d(&map_b, &full_bar[stage], sb + nb * 8192, n0 + nb * 64, kb * BLOCK_K, 0, 0);
-                    } else
-                    tma_load_4d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0, bz0, bz1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                        tma_load_4d(&map_a, &full_bar[stage], sa, c0, c1, c2, c3);
+                        if (p.b_mn) {
+                            #pragma unroll
+                            for (int nb = 0; nb < BLOCK_N / 64; nb++) tma_load_4d(&map_b, &full_bar[stage], sb + nb * 8192, n0 + nb * 64, kb * BLOCK_K, 0, 0);
+                        } else
+                        tma_load_4d(&map_b, &full_bar[stage], sb, kb * BLOCK_K, n0, bz0, bz1);
+                    }
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // whole warp on the (uniform) loop and the barrier waits, one elected lane issues: see elect_one()
+        {
             const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.b_mn);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0), tiles_u = __shfl_sync(0xffffffffu, smem_u32(tiles), 0);
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
                 const int as = it & 1;
                 mbar_wait(&tmem_empty_bar[as], ((uint32_t)(it >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator stage
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+                const uint32_t tmem_d = tmem_u + (uint32_t)(as * BLOCK_N);
                 const int sp = t % p.splits;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(tiles + (size_t)stage * C::kStageBytes);
-                    const uint64_t da = make_sw128_desc(sa), db = p.b_mn ? make_sw128_desc_mn(sa + C::kABytes, 8192u) : make_sw128_desc(sa + C::kABytes);
-                    #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-                        // advancing K inside the 128B swizzle atom = +32 B on the start address (>>4 => +2);
-                        // MN-major B: K runs over rows, 16 rows = 2048 B (>>4 => +128)
-                        umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(p.b_mn ? 128 * k : 2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    if (elect_one()) {
+                        const uint32_t sa = tiles_u + (uint32_t)stage * (uint32_t)C::kStageBytes;
+                        const uint64_t da = make_sw128_desc(sa), db = p.b_mn ? make_sw128_desc_mn(sa + C::kABytes, 8192u) : make_sw128_desc(sa + C::kABytes);
+                        #pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                            // advancing K inside the 128B swizzle atom = +32 B on the start address (>>4 => +2);
+                            // MN-major B: K runs over rows, 16 rows = 2048 B (>>4 => +128)
+                            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(p.b_mn ? 128 * k : 2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+                        if (kb + 1 == kb1) umma_commit(&tmem_full_bar[as]);               // accumulator complete
                     }
-                    umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full_bar[as]);               // accumulator complete
+                if (kb1 <= kb0) {                                   // empty K-range (the split-K planner never produces one): still release the epilogue
+                    if (elect_one()) umma_commit(&tmem_full_bar[as]);
+                    __syncwarp();
+                }
             }
         }
     } else {

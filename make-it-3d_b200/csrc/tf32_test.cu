@@ -19,7 +19,7 @@ __device__ void stage(const float* __restrict__ X, int R, int C, uint8_t* hi, ui
 // mode 0: D = A[128xK] . B[NxK]^T (both K-major) ; mode 1: D = A'[Kx128]^T . B'[KxN] (both MN-major) ; mode 2: A K-major, B' MN-major
 __global__ void __launch_bounds__(160, 1) k_tf32_tile_test(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K, int mode) {
     extern __shared__ uint8_t smem_dyn[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sm = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS / LDS, not generic ST / LD)
     const int swapv = mode >= 3; if (swapv) mode -= 2;
     const int a_mn = mode == 1, b_mn = mode >= 1;
     const int Ra = a_mn ? K : 128, Ca = a_mn ? 128 : K, Rb = b_mn ? K : N, Cb = b_mn ? N : K;

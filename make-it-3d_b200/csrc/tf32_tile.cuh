@@ -43,6 +43,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// four 4-column chunks, 8 columns apart: v[4j .. 4j+3] = columns taddr + 8j .. + 3 of this thread's TMEM lane; one wait for all four
+__device__ __forceinline__ void tmem_ld4x4(uint32_t taddr, uint32_t (&v)[16]) {
+    #pragma unroll
+    for (int j = 0; j < 4; j++)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3]) : "r"(taddr + 8u * (uint32_t)j));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ int g_swap_lbo_sbo = 0;   // experiment switch used by the unit-test kernel only
 // One operand = (hi base, lo base) of its first block + how to walk it.
 struct Operand { uint32_t hi, lo; uint32_t blk_stride; int mn_major; };
@@ -81,6 +90,7 @@ __device__ __forceinline__ uint32_t issue_3tf32(uint32_t tmem_d, const Operand& 
 namespace fbf {
 using ftc::mbar_arrive;
 using ftc::tmem_ld16;
+using ftc::tmem_ld4x4;
 
 // byte offset of element (row, c) inside a [rows x 64 bf16] tile
 __device__ __forceinline__ uint32_t sw_off16(int row, int c) {
@@ -93,12 +103,25 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16&
     m = __float2bfloat16_rn(r1);
     l = __float2bfloat16_rn(r1 - __bfloat162float(m));
 }
+// Two values at a time: one packed conversion (F2FP.BF16.F32.PACK_AB, full-rate ALU) per part instead of two scalar F2F.BF16.F32, which
+// issue at a quarter of that rate -- the chain kernel's owners convert 576 values per evaluation and were bound by that pipe.
+// Same round-to-nearest-even as split3: bit-identical parts.  x0 lands in the low half (the lower column / K index).
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void split3x2(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
+    h = pack_bf16x2(x0, x1);
+    const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xffff0000u);
+    m = pack_bf16x2(r0, r1);
+    l = pack_bf16x2(r0 - __uint_as_float(m << 16), r1 - __uint_as_float(m & 0xffff0000u));
+}
 // pack 8 floats into one 16-byte chunk per part
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& ph, uint4& pm, uint4& pl) {
-    __align__(16) __nv_bfloat16 h[8], m[8], l[8];
+    uint32_t h[4], m[4], l[4];
     #pragma unroll
-    for (int i = 0; i < 8; i++) split3(x[i], h[i], m[i], l[i]);
-    ph = *reinterpret_cast<const uint4*>(h); pm = *reinterpret_cast<const uint4*>(m); pl = *reinterpret_cast<const uint4*>(l);
+    for (int i = 0; i < 4; i++) split3x2(x[2 * i], x[2 * i + 1], h[i], m[i], l[i]);
+    ph = make_uint4(h[0], h[1], h[2], h[3]); pm = make_uint4(m[0], m[1], m[2], m[3]); pl = make_uint4(l[0], l[1], l[2], l[3]);
 }
 // kind::f16 instruction descriptor with BF16 operands (format 1), fp32 accumulate
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
@@ -109,14 +132,22 @@ struct Operand { uint32_t base; uint32_t part_stride; uint32_t lbo; int mn_major
 
 // D[128 x N] (+)= A . B over K elements (K % 16 == 0; K-major operands: K <= 64).  Six MMAs per K = 16 step keep every
 // product term down to 2^-16 of the leading one: hh, hm, mh, hl, lh, mm  -> fp32-class accuracy.
+// The descriptors of one operand differ only in the 14-bit start-address field: one base descriptor per operand, then a 32-bit add of
+// (byte offset >> 4) per use (all tiles live below 256 KB, the field cannot carry into the LBO field).
 __device__ __forceinline__ uint32_t issue_bf16x3(uint32_t tmem_d, const Operand& A, const Operand& B, int K, uint32_t idesc, uint32_t acc) {
+    const uint64_t a0 = ftc::desc_sw128(A.base, A.mn_major ? A.lbo : 16u), b0 = ftc::desc_sw128(B.base, B.mn_major ? B.lbo : 16u);
+    const uint32_t a_lo = (uint32_t)a0, b_lo = (uint32_t)b0;
+    const uint64_t a_hi = a0 & 0xFFFFFFFF00000000ull, b_hi = b0 & 0xFFFFFFFF00000000ull;
+    #pragma unroll
     for (int k16 = 0; k16 < K / 16; k16++) {
-        const uint32_t oa = A.mn_major ? (uint32_t)k16 * 2048u : (uint32_t)k16 * 32u;
-        const uint32_t ob = B.mn_major ? (uint32_t)k16 * 2048u : (uint32_t)k16 * 32u;
-        const uint32_t la = A.mn_major ? A.lbo : 16u, lb = B.mn_major ? B.lbo : 16u;
+        const uint32_t oa = (A.mn_major ? (uint32_t)k16 * 2048u : (uint32_t)k16 * 32u) >> 4;
+        const uint32_t ob = (B.mn_major ? (uint32_t)k16 * 2048u : (uint32_t)k16 * 32u) >> 4;
         uint64_t da[3], db[3];
         #pragma unroll
-        for (int q = 0; q < 3; q++) { da[q] = ftc::desc_sw128(A.base + q * A.part_stride + oa, la); db[q] = ftc::desc_sw128(B.base + q * B.part_stride + ob, lb); }
+        for (int q = 0; q < 3; q++) {
+            da[q] = a_hi | (uint64_t)(a_lo + oa + q * (A.part_stride >> 4));
+            db[q] = b_hi | (uint64_t)(b_lo + ob + q * (B.part_stride >> 4));
+        }
         tc::umma_f16(tmem_d, da[0], db[0], idesc, acc); acc = 1;
         tc::umma_f16(tmem_d, da[0], db[1], idesc, 1);
         tc::umma_f16(tmem_d, da[1], db[0], idesc, 1);

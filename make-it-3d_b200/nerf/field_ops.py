@@ -62,6 +62,7 @@ def _cfg_struct(cfg, light_d):
     c.n_evals = cfg["n_evals"]; c.shading = L.SHADING[cfg["shading"]]; c.ambient_ratio = cfg["ambient_ratio"]
     c.light_d = light_d.data_ptr() if light_d is not None else None
     c.impl = L.FIELD_IMPL[cfg.get("impl", "tcgen05")]
+    c.scatter_agg_scale = float(cfg.get("scatter_agg_scale", 0.0))
     return c
 
 

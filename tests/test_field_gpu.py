@@ -108,7 +108,7 @@ def test_density_matches_oracle_and_k1_backward():
     assert max_abs(net.sigma_net.net[1].weight.grad.cpu(), q) / float(q.abs().max()) < 1e-3
 
 
-@pytest.mark.parametrize("impl", ["tcgen05", "ffma", "tcgen05_fused_scatter", "tcgen05_split_scatter"])
+@pytest.mark.parametrize("impl", ["tcgen05", "ffma", "tcgen05_fused_scatter", "tcgen05_split_scatter", "tcgen05_single_e"])
 @pytest.mark.parametrize("case", ["albedo", "lambertian", "textureless"])
 def test_fused_render_step_matches_reference_golden(case, impl):
     """The drop-in call Trainer.train_step makes (model.render(...), nerf/utils.py:496) on the fused CUDA path vs the
