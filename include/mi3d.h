@@ -168,7 +168,7 @@ typedef struct {
     float ambient_ratio;
     const float* light_d; /* device [3] (multi-view batches: [n_views][3]), needed unless shading == albedo */
     int impl;             /* MI3D_FIELD_IMPL_* (explicit: the library reads no environment variables) */
-    float scatter_agg_scale; /* tuning knob of the fused scatter: REDs of hash-grid levels with scale below this are warp-aggregated; 0 = library default (50) */
+    float scatter_agg_scale; /* tuning knob of the fused scatter: REDs of hash-grid levels with scale below this are warp-aggregated; 0 = library default (100) */
 } mi3d_field_cfg;
 
 /* Multi-view batches (several camera views' rays in one march: ray-parallel multi-GPU render, or several views per GPU).

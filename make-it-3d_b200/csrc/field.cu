@@ -1894,7 +1894,7 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
     a.tape = tape; a.g_sigmas = grad_sigmas; a.g_rgbs = grad_rgbs; a.g_normals = grad_normals;
     a.g_loss_orient = grad_loss_orient; a.g_loss_smooth = grad_loss_smooth;
     a.g_table = grad_table; a.g_mlp = *grad_mlp;
-    a.enc_buf = nullptr; a.denc_buf = nullptr; a.tile0 = 0; a.tile1 = 0xFFFFFFFFu; a.agg_scale_max = 50.f;
+    a.enc_buf = nullptr; a.denc_buf = nullptr; a.tile0 = 0; a.tile1 = 0xFFFFFFFFu; a.agg_scale_max = 100.f;
     a.e_pingpong = cfg->impl != MI3D_FIELD_IMPL_TCGEN05_SINGLE_E && cfg->impl != MI3D_FIELD_IMPL_TCGEN05_SPLIT_SCATTER;
     a.segs = io->segs; a.noise_mode = io->noise_mode;
     if ((io->segs || io->noise_mode) && cfg->impl == MI3D_FIELD_IMPL_FFMA) return MI3D_ERR_ARG;
@@ -1915,10 +1915,12 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
                 // full 13-evaluation backward 8.2 ms split vs 5.8 ms fused; 7-evaluation backward 3.7 vs 3.4; centre-only (SDS) 0.91 vs 0.89.
                 // The RED stream is LSU-issue-bound (1.29 cycles per lane), the chain is latency-bound: they overlap in one kernel.
                 const bool fuse = cfg->impl != MI3D_FIELD_IMPL_TCGEN05_SPLIT_SCATTER;
-                // inside the chain kernel the 5-step shuffle scans of the warp aggregation compete with the owner warps for issue slots:
-                // aggregate only levels 0-3 (scale < 50, cells >= 7 march steps wide).  Measured (M = 424 k, full backward): threshold 200 ->
-                // 5.79 ms, 120 -> 5.56, 60 -> 5.29, 50 -> 5.36, 25 -> 6.74, no aggregation -> 11.7 (same-address RED serialisation in L2)
-                a.agg_scale_max = cfg->scatter_agg_scale > 0.f ? cfg->scatter_agg_scale : 50.f;
+                // Which levels' REDs are warp-aggregated inside the chain kernel.  The scans cost issue slots next to the owner warps, the REDs
+                // they remove are the ones that serialise in L2 (the benchmark scene concentrates every sample in a sphere of radius 0.2:
+                // ~2 k occupied cells at level 5).  Measured, M = 424 k, full backward (tools/prof_render.py --agg): no aggregation 11.7 ms;
+                // round-2a kernel: 25 -> 6.74, 50 -> 5.36, 60 -> 5.29, 120 -> 5.56, 200 -> 5.79; with the elected-lane MMA issue, packed
+                // splits and both scatter halves sharing the coarse levels: 25 -> 6.44, 50 -> 5.02, 100 -> 4.81, 200 -> 4.93.
+                a.agg_scale_max = cfg->scatter_agg_scale > 0.f ? cfg->scatter_agg_scale : 100.f;
                 if (fuse) {
                     // the chain kernel's encoder warps scatter d(enc) themselves, straight from TMEM: the RED stream (LSU-bound) runs
                     // under the MMA / epilogue chain (latency-bound) of the next evaluation instead of in a kernel of its own

@@ -202,7 +202,7 @@ struct Engine {
         const int ppc = (HW + chunks - 1) / chunks; chunks = (HW + ppc - 1) / ppc;
         const __half* xp = x.p; __half* yp = y.p; const GN gg = g;
         push([=](cudaStream_t st) {
-            sdk::k_gn_stats<<<dim3(chunks, N), threads, (size_t)2 * PL * C * sizeof(float), st>>>(xp, HW, C, G, ppc, gg.stats);
+            sdk::k_gn_stats<<<dim3(chunks, N), threads, sdk::gn_smem_bytes(PL, C, G), st>>>(xp, HW, C, G, ppc, gg.stats);
             sdk::k_gn_apply<<<dim3(chunks, N), threads, 0, st>>>(xp, yp, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, ppc);
             return (int)cudaGetLastError();
         });
@@ -218,7 +218,7 @@ struct Engine {
         const int ppc = (HW + chunks - 1) / chunks; chunks = (HW + ppc - 1) / ppc;
         const GN gg = g;
         push([=](cudaStream_t st) {
-            sdk::k_gn_bwd_stats<<<dim3(chunks, N), threads, (size_t)2 * PL * C * sizeof(float), st>>>(gg.x.p, dy, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, ppc, bstats);
+            sdk::k_gn_bwd_stats<<<dim3(chunks, N), threads, sdk::gn_smem_bytes(PL, C, G), st>>>(gg.x.p, dy, gg.stats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, ppc, bstats);
             sdk::k_gn_bwd_apply<<<dim3(chunks, N), threads, 0, st>>>(gg.x.p, dy, gg.stats, bstats, gg.gamma, gg.beta, HW, C, G, gg.eps, gg.silu, add, dx, ppc);
             return (int)cudaGetLastError();
         });

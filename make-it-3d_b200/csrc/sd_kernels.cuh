@@ -73,6 +73,27 @@ __device__ __forceinline__ void gn_group_consts(const double* __restrict__ stats
     }
 }
 
+// Fold the per-thread partial sums sm[PL][C][2] of one CTA into its (group) totals and add them to out[G][2], in a FIXED order (run-to-run
+// deterministic): thread (g, q) first sums the group's channels of pixel lane q, then thread g sums the PL lanes.  (One thread per group
+// walking all cpg x PL slots serially was ~45 % of these kernels' duration on the U-Net shapes: ncu source view, F2F.F64 / DADD chain.)
+// Dynamic shared memory: 2 * PL * C floats + 2 * G * PL doubles (gn_smem_bytes).
+__device__ __forceinline__ void gn_fold(const float* sm, int C, int G, int cpg, int PL, double* __restrict__ out) {
+    double* part = reinterpret_cast<double*>(const_cast<float*>(sm) + (((size_t)2 * PL * C + 1) & ~(size_t)1));
+    for (int t = threadIdx.x; t < G * PL; t += blockDim.x) {
+        const int g = t / PL, q = t - g * PL;
+        double a = 0, b = 0;
+        for (int c = g * cpg; c < (g + 1) * cpg; c++) { a += sm[2 * (q * C + c)]; b += sm[2 * (q * C + c) + 1]; }
+        part[2 * t] = a; part[2 * t + 1] = b;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double a = 0, b = 0;
+        for (int q = 0; q < PL; q++) { a += part[2 * (g * PL + q)]; b += part[2 * (g * PL + q) + 1]; }
+        atomicAdd(&out[2 * g], a); atomicAdd(&out[2 * g + 1], b);
+    }
+}
+inline size_t gn_smem_bytes(int PL, int C, int G) { return ((((size_t)2 * PL * C + 1) & ~(size_t)1) * sizeof(float)) + (size_t)2 * G * PL * sizeof(double); }
+
 __global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, int pix_per_cta, double* __restrict__ stats /*[N][G][2]*/) {
     extern __shared__ float sm[];                 // [PL][C][2]: one slot per thread, folded in a FIXED order (run-to-run deterministic)
     const int n = blockIdx.y, cpg = C / G, VPP = C / 8, PL = blockDim.x / VPP;
@@ -107,12 +128,7 @@ __global__ void k_gn_stats(const __half* __restrict__ x, int HW, int C, int G, i
         for (int k = 0; k < 8; k++) { sm[2 * (pl * C + cv * 8 + k)] = s[k]; sm[2 * (pl * C + cv * 8 + k) + 1] = ss[k]; }
     }
     __syncthreads();
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        double a = 0, b = 0;
-        for (int c = g * cpg; c < (g + 1) * cpg; c++)
-            for (int q = 0; q < PL; q++) { a += sm[2 * (q * C + c)]; b += sm[2 * (q * C + c) + 1]; }
-        atomicAdd(&stats[((size_t)n * G + g) * 2], a); atomicAdd(&stats[((size_t)n * G + g) * 2 + 1], b);
-    }
+    gn_fold(sm, C, G, cpg, PL, stats + (size_t)n * G * 2);
 }
 
 // y = act((x - mean) * rstd * gamma + beta); same (chunks, N) grid and thread mapping as k_gn_stats
@@ -196,12 +212,7 @@ __global__ void k_gn_bwd_stats(const __half* __restrict__ x, const __half* __res
         for (int k = 0; k < 8; k++) { sm[2 * (pl * C + cv * 8 + k)] = s1[k]; sm[2 * (pl * C + cv * 8 + k) + 1] = s2[k]; }
     }
     __syncthreads();
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        double a = 0, b = 0;
-        for (int c = g * cpg; c < (g + 1) * cpg; c++)
-            for (int q = 0; q < PL; q++) { a += sm[2 * (q * C + c)]; b += sm[2 * (q * C + c) + 1]; }
-        atomicAdd(&bstats[((size_t)n * G + g) * 2], a); atomicAdd(&bstats[((size_t)n * G + g) * 2 + 1], b);
-    }
+    gn_fold(sm, C, G, cpg, PL, bstats + (size_t)n * G * 2);
 }
 // pass 2: dx = rstd * (dg - mean(dg) - xhat * mean(dg*xhat)) (+ add, optional accumulation of another gradient branch)
 __global__ void k_gn_bwd_apply(const __half* __restrict__ x, const __half* __restrict__ dy, const double* __restrict__ stats,
