@@ -311,3 +311,20 @@ def test_update_extra_state_matches_reference_golden():
     bits = net.density_bitfield.cpu().numpy()
     diff = np.unpackbits(bits ^ z["bitfield"]).sum()
     assert diff <= 2, diff            # a cell sitting on the threshold (mean density, 4.7358) may flip with the last bit of sigma
+
+
+def test_update_extra_state_with_shared_seed_is_replica_identical():
+    """Multi-GPU invariant (parallel.py): every rank refreshes its own copy of the density grid with `seed=shared_seed(...)` and no
+    broadcast follows, so two replicas holding the same parameters must end with BIT-identical grids and bitfields -- and a different
+    seed must move the jittered cell positions (the jitter used to come from the process-global CPU generator)."""
+    par = importlib.import_module("make-it-3d_b200.parallel")
+    g = load_golden("render_albedo.npz")
+    nets = [_net_from_golden(g) for _ in range(3)]
+    for i, (net, seed) in enumerate(zip(nets, (par.shared_seed(3, 16), par.shared_seed(3, 16), par.shared_seed(3, 32)))):
+        torch.manual_seed(100 + i)                      # the global generators differ between replicas, like between ranks
+        net.update_extra_state(decay=0.95, seed=seed)
+        net.update_extra_state(decay=0.95, seed=seed + 1)
+    a, b, c = nets
+    assert torch.equal(a.density_grid, b.density_grid) and torch.equal(a.density_bitfield, b.density_bitfield)
+    assert float(a.mean_density) == float(b.mean_density)
+    assert not torch.equal(a.density_grid, c.density_grid)

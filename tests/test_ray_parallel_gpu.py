@@ -92,6 +92,11 @@ def _worker(rank, world, port, result):
         res["seq"] = seq
         res["seq_g_table"] = net.encoder.params.grad.detach().cpu()
         res["seq_g_mlp"] = [p.grad.detach().cpu() for p in net.sigma_net.parameters()]
+    # replicas refresh the occupancy grid themselves with a seed every rank shares: no broadcast, identical bitfields (parallel.py)
+    net.update_extra_state(decay=0.95, seed=par.shared_seed(3, 16))
+    torch.cuda.synchronize()
+    res["bitfield"] = net.density_bitfield.cpu()
+    res["grid"] = net.density_grid.cpu()
     result[rank] = res
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
@@ -119,4 +124,5 @@ def test_two_rank_ray_parallel_step_equals_sequential_accumulation():
     assert seq[0]["marched"] > 1.1 * seq[1]["marched"]
     assert r0["marched"] + r1["marched"] == seq[0]["marched"] + seq[1]["marched"]
     assert abs(r0["marched"] - r1["marched"]) < 0.03 * (r0["marched"] + r1["marched"])
+    assert torch.equal(r0["bitfield"], r1["bitfield"]) and torch.equal(r0["grid"], r1["grid"])
     print(f"samples: views {seq[0]['marched']} / {seq[1]['marched']}  ->  ranks {r0['marched']} / {r1['marched']}")

@@ -64,8 +64,16 @@ def main():
         r = agg.setdefault(name[:70], [0, 0.0])
         r[0] += 1; r[1] += d
         tr = ev.time_range
-        ivals.append((tr.start, tr.end))
+        ivals.append((tr.start, tr.end, name[:48]))
     ivals.sort()
+    # idle gaps between consecutive kernels (where the host, not the GPU, paces the step)
+    gaps, last_e, last_n = [], None, None
+    for s_, e_, n_ in ivals:
+        if last_e is not None and s_ > last_e:
+            gaps.append((s_ - last_e, last_n, n_))
+        if last_e is None or e_ > last_e:
+            last_e, last_n = e_, n_
+    ivals = [(s_, e_) for s_, e_, _ in ivals]
     busy, cur_s, cur_e = 0.0, None, None
     for s_, e_ in ivals:
         if cur_e is None or s_ > cur_e:
@@ -84,6 +92,12 @@ def main():
     print(f"{'kernel':70s} {'n/step':>7s} {'us/step':>9s} {'mean us':>8s} {'share':>6s}")
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{k:70s} {n / a.steps:7.1f} {us / a.steps:9.1f} {us / n:8.1f} {100 * us / tot:5.1f}%")
+    gagg = collections.OrderedDict()
+    for g_, a_, b_ in gaps:
+        r = gagg.setdefault((a_, b_), [0, 0.0]); r[0] += 1; r[1] += g_
+    print(f"# idle gaps: {sum(g for g, _, _ in gaps) / a.steps / 1e3:.3f} ms/step in {len(gaps) / a.steps:.0f} gaps/step; largest (after kernel -> before kernel):")
+    for (a_, b_), (n, us) in sorted(gagg.items(), key=lambda kv: -kv[1][1])[:14]:
+        print(f"#   {us / a.steps:8.1f} us/step  n/step {n / a.steps:5.1f}  {a_}  ->  {b_}")
 
 
 if __name__ == "__main__":
