@@ -127,3 +127,37 @@ def vae_encode_moments(sd, x, groups=32):
     h = _conv(_gn_silu(h, sd, "encoder.conv_norm_out", groups, 1e-6), sd, "encoder.conv_out")
     mean, logvar = _conv(h, sd, "quant_conv", padding=0).chunk(2, dim=1)
     return mean, logvar.clamp(-30.0, 20.0)
+
+
+def _vae_mid(h, sd, p, groups):
+    """mid block of the VAE encoder / decoder: resnet, single-head attention over all channels, resnet"""
+    h = _resnet(h, sd, p + ".resnets.0", groups, 1e-6)
+    a = p + ".attentions.0"
+    B, Cc, H, W = h.shape
+    tok = F.group_norm(h, groups, sd[a + ".group_norm.weight"], sd[a + ".group_norm.bias"], 1e-6).flatten(2).transpose(1, 2)
+    h = h + _mha(tok, tok, sd, a, head_dim=Cc).transpose(1, 2).reshape(B, Cc, H, W)
+    return _resnet(h, sd, p + ".resnets.1", groups, 1e-6)
+
+
+def vae_decode(sd, z, groups=32):
+    """AutoencoderKL.decode(z).sample (nerf/sd.py:205): post_quant_conv (1x1), decoder.conv_in, mid block, up blocks (every resnet of a
+    block, then nearest-2x + conv where the block has an upsampler), GroupNorm + SiLU + conv_out; names as in AutoencoderKL.state_dict()."""
+    h = _conv(_conv(z, sd, "post_quant_conv", padding=0), sd, "decoder.conv_in")
+    h = _vae_mid(h, sd, "decoder.mid_block", groups)
+    for i in range(_count(sd, r"decoder\.up_blocks\.(\d+)\.")):
+        for j in range(_count(sd, rf"decoder\.up_blocks\.{i}\.resnets\.(\d+)\.")):
+            h = _resnet(h, sd, f"decoder.up_blocks.{i}.resnets.{j}", groups, 1e-6)
+        if f"decoder.up_blocks.{i}.upsamplers.0.conv.weight" in sd:
+            h = _conv(F.interpolate(h, scale_factor=2.0, mode="nearest"), sd, f"decoder.up_blocks.{i}.upsamplers.0.conv")
+    return _conv(_gn_silu(h, sd, "decoder.conv_norm_out", groups, 1e-6), sd, "decoder.conv_out")
+
+
+def ddim_prev_sample(eps, t, x_t, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
+    """DDIMScheduler.step (eta = 0, epsilon prediction, no clipping, set_alpha_to_one = False) for prev = t - 1, written from the
+    closed form  x_{t-1} = sqrt(a_prev / a_t) x_t + (sqrt(1 - a_prev) - sqrt(a_prev (1 - a_t) / a_t)) eps  in float64."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float64) ** 2
+    ac = torch.cumprod(1.0 - betas, 0)
+    a_t, a_p = ac[t], ac[max(t - 1, 0)]
+    c_x = math.sqrt(float(a_p / a_t))
+    c_e = math.sqrt(float(1 - a_p)) - math.sqrt(float(a_p * (1 - a_t) / a_t))
+    return (c_x * x_t.double() + c_e * eps.double()).to(x_t.dtype)

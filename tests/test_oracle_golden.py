@@ -150,6 +150,20 @@ def test_sd_oracle_two_independent_restatements_agree():
         mb, lb = sd_ref2.vae_encode_moments(vae.state_dict(), img)
     assert float((a - b).abs().max()) < 2e-5 * float(a.abs().max())
     assert float((ma - mb).abs().max()) < 2e-5 * float(ma.abs().max()) and float((la - lb).abs().max()) < 2e-5 * max(1.0, float(la.abs().max()))
+    # the "denoise" side branch (nerf/sd.py:153-159, 201-210): VAE decoder and the DDIM t -> t-1 step, restated both ways
+    dec = sd_ref.AutoencoderKLDecoder(vcfg).eval()
+    with torch.no_grad():
+        for m in dec.modules():
+            if isinstance(m, torch.nn.GroupNorm):
+                m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.3, 0.3)
+        z = torch.randn(1, vcfg["latent_channels"], 8, 8, generator=g)
+        da, db = dec(z), sd_ref2.vae_decode(dec.state_dict(), z, groups=vcfg["groups"])
+    assert da.shape == (1, 3, 8 * 2 ** (len(vcfg["block_out"]) - 1), 8 * 2 ** (len(vcfg["block_out"]) - 1))
+    assert float((da - db).abs().max()) < 2e-5 * float(da.abs().max())
+    eps, xt = torch.randn(1, 4, 8, 8, generator=g), torch.randn(1, 4, 8, 8, generator=g)
+    for t in (1, 37, 399, 0):
+        pa, pb = sd_ref.ddim_step_ref(eps, t, xt), sd_ref2.ddim_prev_sample(eps, t, xt)
+        assert float((pa - pb).abs().max()) < 1e-5 * float(pa.abs().max())
     # published sizes: stabilityai/stable-diffusion-2-base unet 865 910 724 parameters; SD VAE encoder + quant_conv 34 163 664
     with torch.device("meta"):
         big_u = sd_ref.UNet2DConditionModel(sd_ref.sd20_unet_config())
