@@ -226,9 +226,10 @@ int mi3d_field_backward(const mi3d_field_io* io, const float* table, const mi3d_
                         const mi3d_field_cfg* cfg, const float* tape, const float* grad_sigmas, const float* grad_rgbs,
                         const float* grad_normals, const float* grad_loss_orient, const float* grad_loss_smooth,
                         float* grad_table, const mi3d_mlp_grad* grad_mlp, void* workspace, mi3d_stream_t stream);
-/* workspace (nullable): mi3d_field_backward_workspace_bytes() bytes of scratch.  When given, the backward runs as a three-kernel
- * pipeline per chunk of 1 048 576 samples (full-occupancy gather -> tensor-core chain -> full-occupancy warp-aggregated scatter);
- * when NULL everything stays in one kernel (slower: the gather/scatter warps are starved). */
+/* workspace (nullable): mi3d_field_backward_workspace_bytes() bytes of scratch.  When given, the backward runs per chunk of 1 048 576
+ * samples: encodings come from io->enc_cache or from a full-occupancy gather kernel into the scratch, then the tensor-core chain kernel
+ * runs and issues the table-gradient REDs itself (cfg->impl = _SPLIT_SCATTER: a separate full-occupancy scatter kernel instead).
+ * When NULL the chain kernel also gathers in-kernel (slower: its eight gather warps are starved); the Python host always passes scratch. */
 size_t mi3d_field_backward_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------------------------------------
