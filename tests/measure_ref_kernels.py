@@ -2,7 +2,7 @@
 exactly like raymarching/raymarching.py:173-303 drives them: 268 MB zero-fill, .item() host sync, zeros_like for the gradients)
 timed beside the mi3d kernels on the bench's rays (128x128, sphere r = 0.2, front view: M ~ 635 k samples).  CUDA events, median
 of 20, legacy default stream for the reference (its launches use <<<g,b>>> with no stream).  TEST/MEASUREMENT TOOL, not product.
-    python tools/time_ref_kernels.py > profiles/r2_ref_kernels.txt       (GPU box)"""
+    python tests/measure_ref_kernels.py > profiles/r2_ref_kernels.txt       (GPU box)"""
 import ctypes as C
 import importlib
 import os
