@@ -2,6 +2,7 @@
 Usage (GPU box): python tools/prof_render.py [--hw 128] [--evals 13] [--iters 10]"""
 import argparse
 import importlib
+import math
 import os
 import sys
 
@@ -10,8 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import camera_rays, make_table, sphere_bitfield  # noqa: E402
+import bench  # noqa: E402      (oracle-free input builders: orbit_pose, sphere_bitfield_numpy)
 
 
 def main():
@@ -29,11 +29,15 @@ def main():
     torch.manual_seed(0)
     net = nt.NeRFNetwork(opt).cuda().train()
     with torch.no_grad():
-        net.encoder.params.copy_(torch.from_numpy(make_table(net.encoder.params.numel(), 3, 0.5)))
-    net.density_bitfield = torch.from_numpy(sphere_bitfield(args.radius)).cuda()
-    ro, rd, sc = camera_rays(args.hw)
-    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    ro, rd, sc = cu(ro)[None], cu(rd)[None], cu(sc)[None]
+        table = ((np.random.default_rng(3).random(net.encoder.params.numel(), dtype=np.float32) * 2 - 1) * 0.5).astype(np.float32)
+        net.encoder.params.copy_(torch.from_numpy(table))
+    net.density_bitfield = torch.from_numpy(bench.sphere_bitfield_numpy(args.radius)).cuda()
+    # camera radius 1.25, theta 80, phi 170, fovy 20 (the camera of the parity tests' fixtures), rays from the product's own k_get_rays
+    utils = importlib.import_module("make-it-3d_b200.nerf.utils")
+    pose = torch.from_numpy(bench.orbit_pose(1.25, 80.0, 170.0))[None].cuda()
+    focal = args.hw / (2 * math.tan(math.radians(20.0) / 2))
+    rays = utils.get_rays(pose, (focal, focal, args.hw / 2, args.hw / 2), args.hw, args.hw, -1)
+    ro, rd, sc = rays["rays_o"], rays["rays_d"], rays["depth_scale"]
     bg = torch.rand(3, device="cuda")
     light = torch.tensor([0.0, 0.6, 0.8], device="cuda")
     gimg = torch.randn(1, args.hw * args.hw, 3, device="cuda")
